@@ -1,0 +1,458 @@
+// dense.cu -- dense PPCA EM step (emStepsFast, reference src/GPLVM/PPCA.hs:54-94) on one shard of
+// observations: generic (any D, M <= GPLVM_MAX_M) kernels, the replicated parameter update and the
+// log-likelihood.  The fused FP64 tensor-core statistics kernel for the benchmark shape lives in
+// dense_dmma.cu; everything else (reduction of partials, update, LL) is shared.
+//
+// Single-pass formulation (X = observation-major view of Y, Xc = X - mean):
+//   prep   : Minv = (s2 I + W^T W)^-1,  A = W Minv,  c = mean^T A                   (PPCA.hs:65-66)
+//   stats  : ez_n = x_n^T A - c  (= Minv W^T xc_n, PPCA.hs:67);
+//            XEz = sum_n x_n ez_n^T, EE = sum_n ez_n ez_n^T, sEz = sum_n ez_n        (PPCA.hs:68-69)
+//   update : XEzc = XEz - mean sEz^T; Ezz = N s2 Minv + EE; W' = XEzc Ezz^-1          (PPCA.hs:69,74)
+//            s2' = (|Xc|^2 - 2 tr(W'^T XEzc) + |W' U^T|^2) / (N D), U = chol(Ezz)     (PPCA.hs:75-80)
+//   loglik : PPCA.hs:83-89 through the determinant lemma / Woodbury (no D x D matrix).
+#include "ppca.cuh"
+
+namespace gplvm {
+
+// ------------------------------------------------------------------------------------------------
+// generic split-K statistics GEMM:  out[r][q] = sum_n row(n, r) * col(n, q)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int TG_R = 64, TG_Q = 64, TG_K = 16;  // tile: 64 rows x 64 cols, 16 observations per chunk
+
+template <int KIND>
+__device__ __forceinline__ double row_value(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Ez,
+                                            int ldez, int D, int MPd, int64_t n, int r) {
+  if (KIND == ROWS_DENSE) {
+    // rows: [0,D) features of X | [D, D+MP) components of ez | D+MP: ones
+    if (r < D) return X[n * ldx + r];
+    if (r < D + MPd) return Ez[n * ldez + (r - D)];
+    return 1.0;
+  } else {
+    // rows: [0,D) observed flag | [D,2D) observed value | 2D: ones
+    if (r < D) return isnan(X[n * ldx + r]) ? 0.0 : 1.0;
+    if (r < 2 * D) {
+      const double v = X[n * ldx + (r - D)];
+      return isnan(v) ? 0.0 : v;
+    }
+    return 1.0;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) stats_gemm_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, int D,
+                                                         int MPd, int R1, int R, int Q1, int Q2,
+                                                         const double* __restrict__ C1, int ldc1, int Cw1,
+                                                         const double* __restrict__ C2, int ldc2,
+                                                         double* __restrict__ partials, int64_t S, int64_t obs_per_split,
+                                                         const double* __restrict__ scal) {
+  if (scal[S_DONE] != 0.0) return;
+  __shared__ double Rs[TG_K][TG_R];
+  __shared__ double Cs[TG_K][TG_Q];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int r0 = blockIdx.x * TG_R, q0 = blockIdx.z * TG_Q;
+  const int Q = (r0 < R1) ? Q1 : Q2;  // a tile that straddles R1 computes Q1 columns and stores per row
+  if (q0 >= Q) return;
+  const int64_t nb = (int64_t)blockIdx.y * obs_per_split;
+  const int64_t ne = min(n_obs, nb + obs_per_split);
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+  for (int64_t nc = nb; nc < ne; nc += TG_K) {
+    // stage 16 observations x 64 rows and x 64 cols
+    for (int e = threadIdx.x; e < TG_K * TG_R; e += 256) {
+      const int o = e / TG_R, rr = e % TG_R;
+      const int64_t n = nc + o;
+      const int r = r0 + rr;
+      Rs[o][rr] = (n < ne && r < R) ? row_value<KIND>(X, ldx, C1, ldc1, D, MPd, n, r) : 0.0;
+    }
+    for (int e = threadIdx.x; e < TG_K * TG_Q; e += 256) {
+      const int o = e / TG_Q, qq = e % TG_Q;
+      const int64_t n = nc + o;
+      const int q = q0 + qq;
+      double v = 0.0;
+      if (n < ne && q < Q) v = (q < Cw1) ? C1[n * ldc1 + q] : C2[n * ldc2 + (q - Cw1)];
+      Cs[o][qq] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < TG_K; ++o) {
+      double rv[4], cv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rv[i] = Rs[o][4 * tx + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cv[j] = Cs[o][4 * ty + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(rv[i], cv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double* out = partials + (int64_t)blockIdx.y * S;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 4 * tx + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = q0 + 4 * ty + j;
+      if (q >= ((r < R1) ? Q1 : Q2)) continue;
+      const int64_t off = (r < R1) ? (int64_t)r * Q1 + q : (int64_t)R1 * Q1 + (int64_t)(r - R1) * Q2 + q;
+      out[off] = acc[i][j];
+    }
+  }
+}
+
+// stats[i] = sum_p partials[p][i] in fixed order p = 0..nparts-1 (deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, double* __restrict__ stats,
+                                                              int64_t S, int nparts, const double* __restrict__ scal) {
+  if (scal && scal[S_DONE] != 0.0) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  double a = 0.0;
+  for (int p = 0; p < nparts; ++p) a += partials[(int64_t)p * S + i];
+  stats[i] = a;
+}
+
+// per-feature moments of the local observations.  mode 0: sum x; 1: sum (x-mean)^2;
+// 2 (masked): [count | sum | sum of squares] over the known entries.
+__global__ void __launch_bounds__(256) moments_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, int D, int mode,
+                                                      const double* __restrict__ mean, double* __restrict__ partials,
+                                                      int64_t S, int64_t obs_per_split) {
+  __shared__ double red[3][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + tx;
+  const int64_t nb = (int64_t)blockIdx.y * obs_per_split, ne = min(n_obs, nb + obs_per_split);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  if (d < D) {
+    const double m = (mode == 1) ? mean[d] : 0.0;
+    for (int64_t n = nb + ty; n < ne; n += 8) {
+      const double v = X[n * ldx + d];
+      if (mode == 0) a0 += v;
+      else if (mode == 1) { const double t = v - m; a0 = fma(t, t, a0); }
+      else if (!isnan(v)) { a0 += 1.0; a1 += v; a2 = fma(v, v, a2); }
+    }
+  }
+  red[0][ty][tx] = a0; red[1][ty][tx] = a1; red[2][ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && d < D) {
+    double* out = partials + (int64_t)blockIdx.y * S;
+    const int nk = (mode == 2) ? 3 : 1;
+    for (int k = 0; k < nk; ++k) {
+      double t = 0.0;
+      for (int j = 0; j < 8; ++j) t += red[k][j][tx];
+      out[(int64_t)k * D + d] = t;
+    }
+  }
+}
+
+// ez_n = x_n^T A - c for the generic path (materialised like the reference's expEznZ, PPCA.hs:67)
+__global__ void __launch_bounds__(256) dense_ez_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, Par p,
+                                                       const double* __restrict__ A, const double* __restrict__ c,
+                                                       double* __restrict__ Ez) {
+  if (p.scal[S_DONE] != 0.0) return;
+  extern __shared__ double sm[];
+  const int MP = p.MP, D = p.D;
+  constexpr int DC = 64;                 // feature chunk
+  double* As = sm;                       // DC x MP
+  double* Xs = sm + DC * MP;             // 32 obs x (DC+1)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // obs, column group
+  const int64_t n = (int64_t)blockIdx.x * 32 + tx;
+  double acc[GPLVM_MAX_M / 8 + 1];
+  const int nj = (MP + 7) / 8;
+#pragma unroll
+  for (int j = 0; j < GPLVM_MAX_M / 8 + 1; ++j) acc[j] = 0.0;
+  for (int d0 = 0; d0 < D; d0 += DC) {
+    const int dc = min(DC, D - d0);
+    for (int e = threadIdx.x; e < dc * MP; e += 256) As[e] = A[(int64_t)d0 * MP + e];
+    for (int e = threadIdx.x; e < 32 * DC; e += 256) {
+      const int o = e / DC, dd = e % DC;
+      const int64_t nn = (int64_t)blockIdx.x * 32 + o;
+      Xs[o * (DC + 1) + dd] = (nn < n_obs && dd < dc) ? X[nn * ldx + d0 + dd] : 0.0;
+    }
+    __syncthreads();
+    for (int dd = 0; dd < dc; ++dd) {
+      const double xv = Xs[tx * (DC + 1) + dd];
+#pragma unroll
+      for (int j = 0; j < GPLVM_MAX_M / 8 + 1; ++j)
+        if (j < nj && ty + 8 * j < MP) acc[j] = fma(xv, As[dd * MP + ty + 8 * j], acc[j]);
+    }
+    __syncthreads();
+  }
+  if (n < n_obs) {
+#pragma unroll
+    for (int j = 0; j < GPLVM_MAX_M / 8 + 1; ++j)
+      if (j < nj && ty + 8 * j < MP) Ez[n * MP + ty + 8 * j] = acc[j] - c[ty + 8 * j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// replicated parameter kernels (single CTA; identical on every GPU after the all-reduce)
+// ------------------------------------------------------------------------------------------------
+
+// Minv = (s2 I + W^T W)^-1 (Cholesky), logdet over the first M pivots, A = W Minv, c = mean^T A.
+// sm: 2 * MP * MP doubles.
+__device__ void dense_prep_block(const Par& p, double* sm) {
+  const int D = p.D, MP = p.MP, M = p.M;
+  double* Mm = sm;
+  double* Mi = sm + MP * MP;
+  const double s2 = p.scal[S_SIGMA2];
+  for (int e = threadIdx.x; e < MP * MP; e += blockDim.x) {
+    const int a = e / MP, b = e % MP;
+    double t = 0.0;
+    for (int d = 0; d < D; ++d) t = fma(p.W[(int64_t)d * MP + a], p.W[(int64_t)d * MP + b], t);
+    Mm[e] = t + ((a == b) ? s2 : 0.0);
+  }
+  __syncthreads();
+  const bool ok = block_cholesky(Mm, MP, MP);
+  if (threadIdx.x == 0) {
+    double ld = 0.0;
+    for (int i = 0; i < M; ++i) ld += log(Mm[i * MP + i]);
+    p.scal[S_LOGDETM] = 2.0 * ld;
+    if (!ok) p.scal[S_ERR] = 1.0;
+  }
+  block_chol_inverse(Mm, Mi, MP, MP);
+  for (int e = threadIdx.x; e < MP * MP; e += blockDim.x) p.Minv[e] = Mi[e];
+  for (int e = threadIdx.x; e < D * MP; e += blockDim.x) {
+    const int d = e / MP, b = e % MP;
+    double t = 0.0;
+    for (int a = 0; a < MP; ++a) t = fma(p.W[(int64_t)d * MP + a], Mi[a * MP + b], t);
+    p.A[e] = t;
+  }
+  __syncthreads();
+  __threadfence_block();
+  for (int b = threadIdx.x; b < MP; b += blockDim.x) {
+    double t = 0.0;
+    for (int d = 0; d < D; ++d) t = fma(p.mu[d], p.A[(int64_t)d * MP + b], t);
+    p.c[b] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) dense_prep_kernel(Par p) {
+  extern __shared__ double sm[];
+  dense_prep_block(p, sm);
+}
+
+// stats layout: XEz [D x MP] | EE [MP x MP] | sEz [MP]
+// sm: 2*MP*MP + 64 doubles
+__global__ void __launch_bounds__(256) dense_update_kernel(Par p, const double* __restrict__ stats) {
+  extern __shared__ double sm[];
+  if (p.scal[S_DONE] != 0.0) return;
+  const int D = p.D, MP = p.MP;
+  double* Ezz = sm;                 // MP x MP -> Cholesky factor L (lower)
+  double* red = sm + 2 * MP * MP;   // 33
+  const double* XEz = stats;
+  const double* EE = stats + (int64_t)D * MP;
+  const double* sEz = EE + MP * MP;
+  const double s2 = p.scal[S_SIGMA2];
+  const double Nd = (double)p.N;
+  for (int e = threadIdx.x; e < MP * MP; e += blockDim.x) Ezz[e] = Nd * s2 * p.Minv[e] + EE[e];
+  __syncthreads();
+  const bool ok = block_cholesky(Ezz, MP, MP);
+  // one thread per feature row: w'_d = Ezz^-1 xezc_d ; accumulate the trace terms and max |dW|
+  double second = 0.0, third = 0.0, maxdw = 0.0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double x[GPLVM_MAX_M], b[GPLVM_MAX_M];
+    const double md = p.mu[d];
+    for (int a = 0; a < MP; ++a) { b[a] = XEz[(int64_t)d * MP + a] - md * sEz[a]; x[a] = b[a]; }
+    chol_solve_vec(Ezz, MP, MP, x);
+    for (int a = 0; a < MP; ++a) {
+      second = fma(x[a], b[a], second);
+      maxdw = fmax(maxdw, fabs(p.W[(int64_t)d * MP + a] - x[a]));
+    }
+    // |U w|^2 with U = L^T:  (L^T w)_a = sum_{k>=a} L[k][a] w_k        (wr = newW U^T, PPCA.hs:76,79)
+    for (int a = 0; a < MP; ++a) {
+      double t = 0.0;
+      for (int k = a; k < MP; ++k) t = fma(Ezz[k * MP + a], x[k], t);
+      third = fma(t, t, third);
+    }
+    for (int a = 0; a < MP; ++a) p.W[(int64_t)d * MP + a] = x[a];
+  }
+  second = 2.0 * block_sum(second, red);
+  third = block_sum(third, red);
+  maxdw = block_max(maxdw, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double news2 = (p.scal[S_TOTAL] - second + third) / (Nd * (double)D);
+    const double dvar = fabs(news2 - s2);
+    p.scal[S_SIGMA2] = news2;
+    p.scal[S_DVAR] = dvar;
+    p.scal[S_MAXDW] = maxdw;
+    p.scal[S_STEPS] += 1.0;
+    if (!ok || !(news2 > 0.0)) p.scal[S_ERR] = 1.0;
+    if (p.scal[S_USETOL] != 0.0 && !(fmax(dvar, maxdw) > p.scal[S_TOL])) p.scal[S_DONE] = 1.0;
+  }
+  __syncthreads();
+  __threadfence_block();
+  dense_prep_block(p, sm);  // parameters for the next E-step (also what the LL pass needs)
+}
+
+// LL = -(N/2) (D log 2pi + log det C + tr(C^-1 S)),  S = Xc Xc^T / (N-1)            (PPCA.hs:87-89)
+//   log det C = (D-M) log s2 + log det(s2 I + W^T W);  tr(C^-1 S) = (tr S - tr(Minv W^T S W)) / s2
+// stats (from a statistics pass with A := W, c := mean^T W): EE = sum_n t_n t_n^T, t_n = W^T xc_n.
+__global__ void dense_ll_kernel(Par p, const double* __restrict__ stats) {
+  if (threadIdx.x != 0) return;
+  const int D = p.D, MP = p.MP, M = p.M;
+  const double* TT = stats + (int64_t)D * MP;
+  const double s2 = p.scal[S_SIGMA2], Nd = (double)p.N;
+  double tr = 0.0;
+  for (int a = 0; a < MP; ++a)
+    for (int b = 0; b < MP; ++b) tr = fma(p.Minv[a * MP + b], TT[b * MP + a], tr);
+  const double trS = p.scal[S_TOTAL] / (Nd - 1.0);
+  const double trCS = (trS - tr / (Nd - 1.0)) / s2;
+  const double logdetC = (double)(D - M) * log(s2) + p.scal[S_LOGDETM];
+  p.scal[S_LL] = -1.0 * (Nd / 2.0) * ((double)D * log(2.0 * M_PI) + logdetC + trCS);
+}
+
+// mean = sums / N ; c for the LL pass
+__global__ void dense_set_mean_kernel(Par p, const double* __restrict__ sums) {
+  for (int d = threadIdx.x + blockIdx.x * blockDim.x; d < p.D; d += blockDim.x * gridDim.x) p.mu[d] = sums[d] / (double)p.N;
+}
+__global__ void dense_set_total_kernel(Par p, const double* __restrict__ sums) {
+  // sums[d] = sum_n (x_nd - mean_d)^2 ; fixed order over features
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int d = 0; d < p.D; ++d) t += sums[d];
+    p.scal[S_TOTAL] = t;
+  }
+}
+// c_ll = mean^T W  (into p.c; restored by the next prep)
+__global__ void dense_ll_c_kernel(Par p) {
+  for (int b = threadIdx.x; b < p.MP; b += blockDim.x) {
+    double t = 0.0;
+    for (int d = 0; d < p.D; ++d) t = fma(p.mu[d], p.W[(int64_t)d * p.MP + b], t);
+    p.c[b] = t;
+  }
+}
+
+int splits_for(int64_t n_obs, int64_t unit, int tiles_xy) {
+  // aim for ~4 CTAs per SM over the whole grid
+  int64_t want = ceil_div(148 * 4, tiles_xy > 0 ? tiles_xy : 1);
+  int64_t maxs = ceil_div(n_obs, unit);
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace
+
+int launch_reduce_partials(ShardState& sh, int64_t S, int nparts) {
+  GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 256), 256, 0, sh.st, sh.partials, sh.stats, S, nparts, sh.par.scal);
+  return GPLVM_OK;
+}
+
+int launch_stats_gemm(ShardState& sh, RowKind kind, int D, int R1, int R, int Q1, int Q2, const double* Cmat, int ldc,
+                      int Cw1, const double* Cmat2, int ldc2, int64_t S) {
+  const int rt = (int)ceil_div(R, TG_R), qt = (int)ceil_div(Q1, TG_Q);
+  int ks = splits_for(sh.n, 1024, rt * qt);
+  if (ks > sh.nparts) ks = sh.nparts;
+  int64_t per = round_up(ceil_div(sh.n, ks), TG_K);
+  ks = (int)ceil_div(sh.n, per);
+  dim3 grid(rt, ks, qt);
+  CUDA_TRY(cudaMemsetAsync(sh.partials, 0, sizeof(double) * S * ks, sh.st));
+  if (kind == ROWS_DENSE)
+    GP_LAUNCH(stats_gemm_kernel<ROWS_DENSE>, grid, 256, 0, sh.st, sh.X, sh.ldx, sh.n, D, sh.par.MP, R1, R, Q1, Q2, Cmat, ldc,
+              Cw1, Cmat2, ldc2, sh.partials, S, per, sh.par.scal);
+  else
+    GP_LAUNCH(stats_gemm_kernel<ROWS_MASKED>, grid, 256, 0, sh.st, sh.X, sh.ldx, sh.n, D, sh.par.MP, R1, R, Q1, Q2, Cmat, ldc,
+              Cw1, Cmat2, ldc2, sh.partials, S, per, sh.par.scal);
+  GP_TRY(launch_reduce_partials(sh, S, ks));
+  return GPLVM_OK;
+}
+
+static int launch_moments(gplvm_ppca_session* s, int mode) {
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    const int ft = (int)ceil_div(s->D, 32);
+    int ks = splits_for(sh.n, 256, ft);
+    if (ks > sh.nparts) ks = sh.nparts;
+    const int64_t per = ceil_div(sh.n, ks);
+    ks = (int)ceil_div(sh.n, per);
+    const int64_t S = 3 * s->D;
+    dim3 grid(ft, ks);
+    GP_LAUNCH(moments_kernel, grid, 256, 0, sh.st, sh.X, sh.ldx, sh.n, (int)s->D, mode, sh.par.mu, sh.partials, S, per);
+    GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 256), 256, 0, sh.st, sh.partials, sh.stats, S, ks,
+              (const double*)nullptr);
+  }
+  return GPLVM_OK;
+}
+
+int moments_pass(gplvm_ppca_session* s, int mode) { return launch_moments(s, mode); }
+
+int dense_init_constants(gplvm_ppca_session* s) {
+  // feature means (Util.hs:159-164 on the transposed matrix), then |Xc|_F^2 (PPCA.hs:77)
+  GP_TRY(launch_moments(s, 0));
+  GP_TRY(session_allreduce_stats(s, s->D));
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(dense_set_mean_kernel, 4, 256, 0, sh.st, sh.par, sh.stats);
+  }
+  GP_TRY(launch_moments(s, 1));
+  GP_TRY(session_allreduce_stats(s, s->D));
+  const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(dense_set_total_kernel, 1, 32, 0, sh.st, sh.par, sh.stats);
+    GP_LAUNCH(dense_prep_kernel, 1, 256, smem, sh.st, sh.par);
+  }
+  return GPLVM_OK;
+}
+
+// statistics pass with projection matrix A (D x MP) and offset c (MP): fills sh.stats (local sums)
+static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double* A, const double* c) {
+  if (s->use_dmma) return dense_dmma_stats(s, sh, A, c);
+  const int MP = s->MP, D = (int)s->D;
+  const size_t smem = sizeof(double) * (64 * MP + 32 * 65);
+  GP_LAUNCH(dense_ez_kernel, (unsigned)ceil_div(sh.n, 32), 256, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, A, c, sh.Ez);
+  const int R = D + MP + 1;
+  return launch_stats_gemm(sh, ROWS_DENSE, D, R, R, MP, MP, sh.Ez, MP, MP, nullptr, 0, s->S);
+}
+
+int dense_enqueue_step(gplvm_ppca_session* s) {
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    if (sh.evk0) CUDA_TRY(cudaEventRecord(sh.evk0, sh.st));
+    GP_TRY(dense_stats_pass(s, sh, sh.par.A, sh.par.c));
+    if (sh.evk1) CUDA_TRY(cudaEventRecord(sh.evk1, sh.st));
+  }
+  GP_TRY(session_allreduce_stats(s, s->S));
+  const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(dense_update_kernel, 1, 256, smem, sh.st, sh.par, sh.stats);
+  }
+  return GPLVM_OK;
+}
+
+int dense_loglik(gplvm_ppca_session* s, double* ll) {
+  // one extra pass with the projection W (A := W, c := mean^T W): EE becomes W^T Xc Xc^T W
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(dense_ll_c_kernel, 1, 64, 0, sh.st, sh.par);
+    // the pass must run even after the tolerance rule has fired: clear DONE around it
+    GP_TRY(dense_stats_pass(s, sh, sh.par.W, sh.par.c));
+  }
+  GP_TRY(session_allreduce_stats(s, s->S));
+  const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(dense_ll_kernel, 1, 32, 0, sh.st, sh.par, sh.stats);
+    GP_LAUNCH(dense_prep_kernel, 1, 256, smem, sh.st, sh.par);  // restore c (and A, Minv) for further steps
+  }
+  ShardState& s0 = s->sh[0];
+  CUDA_TRY(cudaSetDevice(s0.dev));
+  double scal[S_COUNT];
+  CUDA_TRY(cudaMemcpyAsync(scal, s0.par.scal, sizeof scal, cudaMemcpyDeviceToHost, s0.st));
+  CUDA_TRY(cudaStreamSynchronize(s0.st));
+  if (scal[S_ERR] != 0.0) return fail(GPLVM_ERR_NUMERIC, "dense PPCA: matrix not positive definite");
+  *ll = scal[S_LL];
+  return GPLVM_OK;
+}
+
+}  // namespace gplvm

@@ -1,0 +1,481 @@
+// masked.cu -- NaN-masked PPCA EM step (emStepsMissed, reference src/GPLVM/PPCA.hs:96-182).
+//
+// Sufficient-statistics formulation, per observation i with O_i the
+// observed features (old W, mu, s2):
+//   M_i  = (s2 I + W^T W) - sum_{d missing} w_d w_d^T                                  (PPCA.hs:114-115)
+//   b_i  = sum_{d in O_i} w_d (y_id - mu_d);  ez_i = M_i^-1 b_i                         (PPCA.hs:116-117)
+//   A_i  = ez_i ez_i^T + s2 M_i^-1
+// statistics:  S1_d = sum_i o_id ez_i,  S2_d = sum_i o_id y_id ez_i,  G_d = sum_i o_id A_i,  sum_i ez_i
+// update (per feature d, replicated):
+//   mu'_d = (sy_d - w_d . S1_d) / n_d                                                   (PPCA.hs:123)
+//   r_d   = S2_d - mu'_d S1_d ;  w'_d = G_d^-1 r_d                                       (PPCA.hs:133-137)
+//   s2'   = sum_d (syy_d - 2 mu'_d sy_d + mu'_d^2 n_d - 2 w'_d . r_d + w'_d^T G_d w'_d) / #known   (PPCA.hs:140-147)
+// LL (PPCA.hs:149-159) and restore (PPCA.hs:161-168) are separate final passes.
+#include "ppca.cuh"
+
+namespace gplvm {
+int moments_pass(gplvm_ppca_session* s, int mode);
+
+namespace {
+
+constexpr int EW = 8;  // warps per CTA in the per-observation kernels
+
+// In-place lower Cholesky of an n x n matrix in shared memory by ONE warp.  Returns false on a non
+// positive pivot.
+__device__ __forceinline__ bool warp_cholesky(double* a, int n, int lane) {
+  bool ok = true;
+  for (int k = 0; k < n; ++k) {
+    __syncwarp();
+    const double akk = a[k * n + k];
+    if (!(akk > 0.0)) ok = false;
+    const double lkk = sqrt(akk);
+    __syncwarp();
+    for (int i = k + lane; i < n; i += 32) a[i * n + k] = (i == k) ? lkk : a[i * n + k] / lkk;
+    __syncwarp();
+    const int r = n - k - 1;
+    for (int idx = lane; idx < r * r; idx += 32) {
+      const int i = k + 1 + idx / r, j = k + 1 + idx % r;
+      if (j <= i) a[i * n + j] -= a[i * n + k] * a[j * n + k];
+    }
+  }
+  __syncwarp();
+  return ok;
+}
+
+// x <- L^-1 x (forward substitution, column oriented; x in shared memory, all lanes participate)
+__device__ __forceinline__ void warp_forward(const double* L, double* x, int n, int lane) {
+  for (int k = 0; k < n; ++k) {
+    __syncwarp();
+    const double xk = x[k] / L[k * n + k];
+    __syncwarp();
+    if (lane == 0) x[k] = xk;
+    for (int i = k + 1 + lane; i < n; i += 32) x[i] -= L[i * n + k] * xk;
+  }
+  __syncwarp();
+}
+// x <- L^-T x
+__device__ __forceinline__ void warp_backward(const double* L, double* x, int n, int lane) {
+  for (int k = n - 1; k >= 0; --k) {
+    __syncwarp();
+    const double xk = x[k] / L[k * n + k];
+    __syncwarp();
+    if (lane == 0) x[k] = xk;
+    for (int i = lane; i < k; i += 32) x[i] -= L[k * n + i] * xk;
+  }
+  __syncwarp();
+}
+
+// Builds, for observation row x (global, D entries), the masked system of one observation:
+//   Mi (shared, M x M) = C0 - sum_{missing} w w^T,   b (shared, M) = sum_{observed} w_d (x_d - mu_d)
+// returns the number of observed features; yy = sum_{observed} (x_d - mu_d)^2.
+__device__ __forceinline__ int masked_build(const double* __restrict__ x, const Par& p, double* Mi, double* b, int lane,
+                                            double& yy) {
+  const int D = p.D, M = p.M;
+  for (int e = lane; e < M * M; e += 32) Mi[e] = p.Minv[e];  // C0 = s2 I + W^T W
+  double bacc[GPLVM_MAX_M];
+#pragma unroll
+  for (int a = 0; a < GPLVM_MAX_M; ++a) bacc[a] = 0.0;
+  double yacc = 0.0;
+  int cnt = 0;
+  __syncwarp();
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    const double v = (d < D) ? x[d] : 0.0;
+    const bool miss = (d < D) && isnan(v);
+    const unsigned mm = __ballot_sync(0xffffffffu, miss);
+    const unsigned vm = __ballot_sync(0xffffffffu, d < D);
+    cnt += __popc(vm & ~mm);
+    if (d < D && !miss) {
+      const double t = v - p.mu[d];
+      yacc = fma(t, t, yacc);
+      const double* w = p.W + (int64_t)d * M;
+#pragma unroll
+      for (int a = 0; a < GPLVM_MAX_M; ++a)
+        if (a < M) bacc[a] = fma(w[a], t, bacc[a]);
+    }
+    unsigned rem = mm;
+    while (rem) {
+      const int bit = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const double* w = p.W + (int64_t)(d0 + bit) * M;
+      for (int e = lane; e < M * M; e += 32) Mi[e] = fma(-w[e / M], w[e % M], Mi[e]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < GPLVM_MAX_M; ++a)
+    if (a < M) {
+      const double t = warp_sum(bacc[a]);
+      if (lane == 0) b[a] = t;
+    }
+  yy = warp_sum(yacc);
+  __syncwarp();
+  return cnt;
+}
+
+// E-step: one warp per observation; writes ez_i (M) and vech(A_i) (NV) to HBM.
+__global__ void __launch_bounds__(EW * 32) masked_estep_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, Par p,
+                                                              double* __restrict__ Ez, double* __restrict__ Av) {
+  if (p.scal[S_DONE] != 0.0) return;
+  extern __shared__ double sm[];
+  const int M = p.M, NV = p.NV;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* Mi = sm + (size_t)w * (2 * M * M + 2 * M);
+  double* Inv = Mi + M * M;
+  double* b = Inv + M * M;
+  const double s2 = p.scal[S_SIGMA2];
+  const int64_t nw = (int64_t)gridDim.x * EW;
+  for (int64_t n = (int64_t)blockIdx.x * EW + w; n < n_obs; n += nw) {
+    double yy;
+    const int cnt = masked_build(X + n * ldx, p, Mi, b, lane, yy);
+    if (cnt == 0 && lane == 0) p.scal[S_ERR] = 2.0;  // all-NaN observation: unsupported (Util.hs:81)
+    const bool ok = warp_cholesky(Mi, M, lane);
+    if (!ok && lane == 0) p.scal[S_ERR] = 1.0;
+    // ez = (L L^T)^-1 b
+    warp_forward(Mi, b, M, lane);
+    warp_backward(Mi, b, M, lane);
+    // Inv = (L L^T)^-1, one lane per column
+    for (int j = lane; j < M; j += 32) {
+      for (int i = 0; i < M; ++i) {
+        double s = (i == j) ? 1.0 : 0.0;
+        for (int k = j; k < i; ++k) s -= Mi[i * M + k] * Inv[k * M + j];
+        Inv[i * M + j] = (i < j) ? 0.0 : s / Mi[i * M + i];
+      }
+      for (int i = M - 1; i >= 0; --i) {
+        double s = Inv[i * M + j];
+        for (int k = i + 1; k < M; ++k) s -= Mi[k * M + i] * Inv[k * M + j];
+        Inv[i * M + j] = s / Mi[i * M + i];
+      }
+    }
+    __syncwarp();
+    for (int a = lane; a < M; a += 32) Ez[n * M + a] = b[a];
+    // vech (row-wise lower triangle): index(a, c) = a (a+1)/2 + c, c <= a
+    for (int e = lane; e < NV; e += 32) {
+      int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((a + 1) * (a + 2) / 2 <= e) ++a;
+      while (a * (a + 1) / 2 > e) --a;
+      const int c = e - a * (a + 1) / 2;
+      Av[n * NV + e] = fma(b[a], b[c], s2 * Inv[a * M + c]);
+    }
+    __syncwarp();
+  }
+}
+
+// per-feature update, one warp per feature.  stats layout:
+//   block 1: D rows x (M + NV): [S1_d | vech G_d];  block 2: D rows x M: S2_d; then one row sum_i ez_i
+__global__ void __launch_bounds__(EW * 32) masked_update_kernel(Par p, const double* __restrict__ stats, double* __restrict__ scratch) {
+  if (p.scal[S_DONE] != 0.0) return;
+  extern __shared__ double sm[];
+  const int M = p.M, NV = p.NV, D = p.D;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int d = blockIdx.x * EW + w;
+  if (d >= D) return;
+  double* G = sm + (size_t)w * (2 * M * M + 2 * M);
+  double* G0 = G + M * M;
+  double* r = G0 + M * M;
+  double* wold = r + M;
+  const double* S1 = stats + (int64_t)d * (M + NV);
+  const double* Gv = S1 + M;
+  const double* S2 = stats + (int64_t)D * (M + NV) + (int64_t)d * M;
+  for (int e = lane; e < M * M; e += 32) {
+    const int a = e / M, c = e % M;
+    const double v = (c <= a) ? Gv[a * (a + 1) / 2 + c] : Gv[c * (c + 1) / 2 + a];
+    G[e] = v;
+    G0[e] = v;
+  }
+  double dot = 0.0;
+  for (int a = lane; a < M; a += 32) {
+    wold[a] = p.W[(int64_t)d * M + a];
+    dot = fma(wold[a], S1[a], dot);
+  }
+  dot = warp_sum(dot);
+  const double nd = p.nd[d], sy = p.sy[d], syy = p.syy[d];
+  const double mu_new = (sy - dot) / nd;
+  for (int a = lane; a < M; a += 32) r[a] = S2[a] - mu_new * S1[a];
+  __syncwarp();
+  double wr = 0.0;  // w' . r needs r before the solve overwrites it
+  double rsave[(GPLVM_MAX_M + 31) / 32];
+#pragma unroll
+  for (int j = 0; j < (GPLVM_MAX_M + 31) / 32; ++j) rsave[j] = (lane + 32 * j < M) ? r[lane + 32 * j] : 0.0;
+  const bool ok = warp_cholesky(G, M, lane);
+  warp_forward(G, r, M, lane);
+  warp_backward(G, r, M, lane);  // r now holds w'_d
+  double quad = 0.0, mdw = 0.0;
+#pragma unroll
+  for (int j = 0; j < (GPLVM_MAX_M + 31) / 32; ++j) {
+    const int a = lane + 32 * j;
+    if (a < M) {
+      wr = fma(r[a], rsave[j], wr);
+      double t = 0.0;
+      for (int c = 0; c < M; ++c) t = fma(G0[a * M + c], r[c], t);
+      quad = fma(r[a], t, quad);
+      mdw = fmax(mdw, fabs(wold[a] - r[a]));
+      p.W[(int64_t)d * M + a] = r[a];
+    }
+  }
+  wr = warp_sum(wr);
+  quad = warp_sum(quad);
+  mdw = warp_max(mdw);
+  if (lane == 0) {
+    const double cd = syy - 2.0 * mu_new * sy + mu_new * mu_new * nd;
+    scratch[d] = cd - 2.0 * wr + quad;
+    scratch[D + d] = mdw;
+    p.mu[d] = mu_new;
+    if (!ok) p.scal[S_ERR] = 1.0;
+  }
+}
+
+// C0 = s2 I + W^T W into p.Minv (single CTA)
+__device__ void masked_prep_block(const Par& p) {
+  const int D = p.D, M = p.M;
+  const double s2 = p.scal[S_SIGMA2];
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int a = e / M, b = e % M;
+    double t = 0.0;
+    for (int d = 0; d < D; ++d) t = fma(p.W[(int64_t)d * M + a], p.W[(int64_t)d * M + b], t);
+    p.Minv[e] = t + ((a == b) ? s2 : 0.0);
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) masked_prep_kernel(Par p) { masked_prep_block(p); }
+
+__global__ void __launch_bounds__(256) masked_finalize_kernel(Par p, const double* __restrict__ stats, const double* __restrict__ scratch) {
+  if (p.scal[S_DONE] != 0.0) return;
+  __shared__ double red[40];
+  const int D = p.D, M = p.M, NV = p.NV;
+  double a = 0.0, m = 0.0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    a += scratch[d];
+    m = fmax(m, scratch[D + d]);
+  }
+  a = block_sum(a, red);
+  m = block_max(m, red);
+  // mean of the E-step latent means, needed by the restore (meanColumn expX^T, PPCA.hs:162)
+  const double* sez = stats + (int64_t)D * (M + NV) + (int64_t)D * M;
+  for (int b = threadIdx.x; b < M; b += blockDim.x) p.c[b] = sez[b] / (double)p.N;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double s2 = p.scal[S_SIGMA2];
+    const double news2 = a / p.scal[S_KNOWN];
+    const double dvar = fabs(news2 - s2);
+    p.scal[S_SIGMA2] = news2;
+    p.scal[S_DVAR] = dvar;
+    p.scal[S_MAXDW] = m;
+    p.scal[S_STEPS] += 1.0;
+    if (!(news2 > 0.0)) p.scal[S_ERR] = 1.0;
+    if (p.scal[S_USETOL] != 0.0 && !(fmax(dvar, m) > p.scal[S_TOL])) p.scal[S_DONE] = 1.0;
+  }
+  __syncthreads();
+  __threadfence_block();
+  masked_prep_block(p);
+}
+
+// data constants: stats = [n_d | sy_d | syy_d] (all-reduced)
+__global__ void masked_set_constants_kernel(Par p, const double* __restrict__ stats) {
+  const int D = p.D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    p.nd[d] = stats[d];
+    p.sy[d] = stats[D + d];
+    p.syy[d] = stats[2 * D + d];
+    p.mu[d] = 0.0;  // initMu = 0 (PPCA.hs:103)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double k = 0.0;
+    for (int d = 0; d < D; ++d) k += stats[d];
+    p.scal[S_KNOWN] = k;
+  }
+}
+
+// per-observation log-likelihood terms with the CURRENT parameters (PPCA.hs:149-159 via A.4)
+__global__ void __launch_bounds__(EW * 32) masked_ll_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, Par p,
+                                                           double* __restrict__ partials) {
+  extern __shared__ double sm[];
+  __shared__ double wsum[EW];
+  const int M = p.M;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* Mi = sm + (size_t)w * (2 * M * M + 2 * M);
+  double* b = Mi + 2 * M * M;
+  const double s2 = p.scal[S_SIGMA2];
+  const double log2pi = log(2.0 * M_PI), logs2 = log(s2);
+  const int64_t nw = (int64_t)gridDim.x * EW;
+  double acc = 0.0;
+  for (int64_t n = (int64_t)blockIdx.x * EW + w; n < n_obs; n += nw) {
+    double yy;
+    const int cnt = masked_build(X + n * ldx, p, Mi, b, lane, yy);
+    const bool ok = warp_cholesky(Mi, M, lane);
+    if (!ok && lane == 0) p.scal[S_ERR] = 1.0;
+    warp_forward(Mi, b, M, lane);  // t = L^-1 W_i^T yc
+    double tt = 0.0, ld = 0.0;
+    for (int a = lane; a < M; a += 32) {
+      tt = fma(b[a], b[a], tt);
+      ld += log(Mi[a * M + a]);
+    }
+    tt = warp_sum(tt);
+    ld = 2.0 * warp_sum(ld);
+    acc += (double)cnt * log2pi + ((double)(cnt - M) * logs2 + ld) + (yy - tt) / s2;
+    __syncwarp();
+  }
+  if (lane == 0) wsum[w] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < EW; ++i) t += wsum[i];
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void masked_ll_final_kernel(Par p, const double* __restrict__ stats) {
+  if (threadIdx.x == 0) p.scal[S_LL] = -1.0 * stats[0] / 2.0;
+}
+
+// B = W (W^T W)^-1 (W^T W + s2 I)  (D x M) into Wprev;  fm = mu + W zbar (D) into scratch   (PPCA.hs:162-167)
+__global__ void __launch_bounds__(256) masked_restore_prep_kernel(Par p, double* __restrict__ fm) {
+  extern __shared__ double sm[];
+  const int D = p.D, M = p.M;
+  double* WtW = sm;            // M x M -> Cholesky
+  double* Inv = sm + M * M;    // (W^T W)^-1
+  double* F = sm + 2 * M * M;  // Inv * (WtW + s2 I)
+  const double s2 = p.scal[S_SIGMA2];
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int a = e / M, b = e % M;
+    WtW[e] = p.Minv[e] - ((a == b) ? s2 : 0.0);  // C0 - s2 I
+  }
+  __syncthreads();
+  const bool ok = block_cholesky(WtW, M, M);
+  block_chol_inverse(WtW, Inv, M, M);
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int a = e / M, b = e % M;
+    double t = 0.0;
+    for (int k = 0; k < M; ++k) t = fma(Inv[a * M + k], p.Minv[k * M + b], t);  // p.Minv = W^T W + s2 I
+    F[e] = t;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < D * M; e += blockDim.x) {
+    const int d = e / M, b = e % M;
+    double t = 0.0;
+    for (int a = 0; a < M; ++a) t = fma(p.W[(int64_t)d * M + a], F[a * M + b], t);
+    p.Wprev[e] = t;
+  }
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double t = p.mu[d];
+    for (int a = 0; a < M; ++a) t = fma(p.W[(int64_t)d * M + a], p.c[a], t);
+    fm[d] = t;
+  }
+  if (threadIdx.x == 0 && !ok) p.scal[S_ERR] = 1.0;
+}
+
+// out[d][i] = B_d . ez_i + fm_d for a chunk of observations; out is feature-major (D x ld)
+__global__ void __launch_bounds__(256) masked_restore_kernel(Par p, const double* __restrict__ Ez, const double* __restrict__ fm,
+                                                            double* __restrict__ out, int64_t ld, int64_t n_chunk) {
+  const int M = p.M, D = p.D;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double ez[GPLVM_MAX_M];
+  if (i < n_chunk)
+    for (int a = 0; a < M; ++a) ez[a] = Ez[i * M + a];
+  for (int d = 0; d < D; ++d) {
+    if (i < n_chunk) {
+      double t = fm[d];
+      for (int a = 0; a < M; ++a) t = fma(p.Wprev[(int64_t)d * M + a], ez[a], t);
+      out[(int64_t)d * ld + i] = t;
+    }
+  }
+}
+
+size_t warp_scratch_bytes(int M) { return sizeof(double) * (size_t)EW * (2 * M * M + 2 * M); }
+
+}  // namespace
+
+int masked_init_constants(gplvm_ppca_session* s) {
+  GP_TRY(moments_pass(s, 2));
+  GP_TRY(session_allreduce_stats(s, 3 * s->D));
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(masked_set_constants_kernel, 1, 256, 0, sh.st, sh.par, sh.stats);
+    GP_LAUNCH(masked_prep_kernel, 1, 256, 0, sh.st, sh.par);
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    // opt in to > 48 KB of dynamic shared memory for M = 32
+    for (ShardState& sh : s->sh) {
+      CUDA_TRY(cudaSetDevice(sh.dev));
+      CUDA_TRY(cudaFuncSetAttribute(masked_estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(masked_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(masked_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    }
+  }
+  return GPLVM_OK;
+}
+
+int masked_enqueue_step(gplvm_ppca_session* s) {
+  const int M = (int)s->M, NV = s->NV, D = (int)s->D;
+  const size_t smem = warp_scratch_bytes(M);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    if (sh.evk0) CUDA_TRY(cudaEventRecord(sh.evk0, sh.st));
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(sh.n, EW), 148 * 8);
+    GP_LAUNCH(masked_estep_kernel, grid, EW * 32, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, sh.Ez, sh.Av);
+    GP_TRY(launch_stats_gemm(sh, ROWS_MASKED, D, D, 2 * D + 1, M + NV, M, sh.Ez, M, M, sh.Av, NV, s->S));
+    if (sh.evk1) CUDA_TRY(cudaEventRecord(sh.evk1, sh.st));
+  }
+  GP_TRY(session_allreduce_stats(s, s->S));
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(masked_update_kernel, (unsigned)ceil_div(D, EW), EW * 32, smem, sh.st, sh.par, sh.stats, sh.scratch);
+    GP_LAUNCH(masked_finalize_kernel, 1, 256, 0, sh.st, sh.par, sh.stats, sh.scratch);
+  }
+  return GPLVM_OK;
+}
+
+int masked_loglik(gplvm_ppca_session* s, double* ll) {
+  const size_t smem = warp_scratch_bytes((int)s->M);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(sh.n, EW), (int64_t)sh.nparts);
+    GP_LAUNCH(masked_ll_kernel, grid, EW * 32, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, sh.partials);
+    // partials are 1 double per CTA: reduce with S = 1
+    GP_TRY(launch_reduce_partials(sh, 1, (int)grid));
+  }
+  GP_TRY(session_allreduce_stats(s, 1));
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(masked_ll_final_kernel, 1, 32, 0, sh.st, sh.par, sh.stats);
+  }
+  ShardState& s0 = s->sh[0];
+  CUDA_TRY(cudaSetDevice(s0.dev));
+  double scal[S_COUNT];
+  CUDA_TRY(cudaMemcpyAsync(scal, s0.par.scal, sizeof scal, cudaMemcpyDeviceToHost, s0.st));
+  CUDA_TRY(cudaStreamSynchronize(s0.st));
+  if (scal[S_ERR] == 2.0) return fail(GPLVM_ERR_UNSUPPORTED, "missing-data PPCA: an observation has every feature missing");
+  if (scal[S_ERR] != 0.0) return fail(GPLVM_ERR_NUMERIC, "missing-data PPCA: matrix not positive definite");
+  *ll = scal[S_LL];
+  return GPLVM_OK;
+}
+
+int masked_restore(gplvm_ppca_session* s, double* restored, int64_t ld) {
+  const int64_t D = s->D;
+  const int M = (int)s->M;
+  const int64_t first = s->sh[0].n0;
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    double* fm = sh.scratch + 2 * D;
+    GP_LAUNCH(masked_restore_prep_kernel, 1, 256, sizeof(double) * 3 * M * M, sh.st, sh.par, fm);
+    int64_t ch = ((int64_t)32 << 20) / D;
+    ch = std::max<int64_t>(1024, (ch / 32) * 32);
+    ch = std::min(ch, sh.n);
+    double* stage = nullptr;
+    CUDA_TRY(cudaMalloc(&stage, sizeof(double) * (size_t)D * ch));
+    for (int64_t c0 = 0; c0 < sh.n; c0 += ch) {
+      const int64_t cn = std::min(ch, sh.n - c0);
+      GP_LAUNCH(masked_restore_kernel, (unsigned)ceil_div(cn, 256), 256, 0, sh.st, sh.par, sh.Ez + c0 * M, fm, stage, ch, cn);
+      double* dst = restored + (sh.n0 - first) + c0;
+      cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * ld, stage, sizeof(double) * ch, sizeof(double) * cn, D,
+                                        cudaMemcpyDeviceToHost, sh.st);
+      if (e != cudaSuccess) { cudaFree(stage); return fail(GPLVM_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); }
+      CUDA_TRY(cudaStreamSynchronize(sh.st));
+    }
+    CUDA_TRY(cudaFree(stage));
+  }
+  return GPLVM_OK;
+}
+
+}  // namespace gplvm

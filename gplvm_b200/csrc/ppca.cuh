@@ -1,0 +1,99 @@
+// ppca.cuh -- PPCA session state shared by dense.cu / dense_dmma.cu / masked.cu / session.cu.
+#pragma once
+#include "common.cuh"
+
+namespace gplvm {
+
+// scalar slots of the device parameter block
+enum Scal {
+  S_SIGMA2 = 0,   // current sigma^2
+  S_TOTAL = 1,    // dense: |Xc|_F^2 (constant of the data, PPCA.hs:77)
+  S_LOGDETM = 2,  // log det (sigma^2 I + W^T W) over the first M rows
+  S_DVAR = 3,     // |sigma2' - sigma2| of the last step (PPCA.hs:82,170)
+  S_MAXDW = 4,    // max |W - W'| of the last step (PPCA.hs:81,171)
+  S_DONE = 5,     // 1.0 once the Right-tol rule has fired (further steps are no-ops)
+  S_STEPS = 6,    // EM steps executed
+  S_ERR = 7,      // != 0: numeric failure (non positive pivot)
+  S_TOL = 8,      // tolerance of the Right rule (used when S_USETOL != 0)
+  S_USETOL = 9,
+  S_LL = 10,      // log-likelihood written by the finalize kernels
+  S_KNOWN = 11,   // masked: number of known entries (knownVars, PPCA.hs:146)
+  S_ZBAR0 = 12,   // unused
+  S_COUNT = 16
+};
+
+// Device pointers into one shard's parameter block (passed to kernels by value).
+struct Par {
+  double* W;     // D x MP   current W (padded columns are zero)
+  double* mu;    // D        dense: feature means (constant); masked: EM mean
+  double* A;     // D x MP   dense: W * Minv
+  double* Minv;  // MP x MP  dense: (sigma2 I + W^T W)^-1 ; masked: C0 = sigma2 I + W^T W
+  double* c;     // MP       dense: mu^T A
+  double* nd;    // D        masked: number of observations knowing feature d (global)
+  double* sy;    // D        masked: sum of known y_d
+  double* syy;   // D        masked: sum of known y_d^2
+  double* Wprev; // D x MP   masked: scratch for the update (new W before commit)
+  double* scal;  // S_COUNT scalars
+  int D, M, MP, NV;
+  long long N;   // global number of observations
+};
+
+struct ShardState {
+  int dev = 0;
+  cudaStream_t st = nullptr;
+  int64_t n0 = 0, n = 0;  // global begin / local count
+  int64_t ldx = 0;
+  double* X = nullptr;         // n x ldx, observation-major; NaN = missing
+  double* Ez = nullptr;        // n x MP (dense generic path / masked path)
+  double* Av = nullptr;        // masked: n x NV  (vech of A_i = ez ez^T + sigma2 Minv_i)
+  double* parblock = nullptr;  // parameter block
+  double* stats = nullptr;     // packed statistics (all-reduced), `S` doubles
+  double* partials = nullptr;  // nparts x S
+  double* scratch = nullptr;   // per-feature scratch (masked update), D doubles x 4
+  void* tmap = nullptr;        // host copy of the CUtensorMap for X (dense DMMA path)
+  int nparts = 0;
+  Par par;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+};
+
+}  // namespace gplvm
+
+struct gplvm_ppca_session {
+  int64_t D = 0, N = 0, M = 0;
+  int MP = 0, NV = 0;
+  bool missing = false;
+  bool has_data = false, initialised = false;
+  bool use_dmma = false;   // dense: fused DMMA kernel eligible
+  int64_t S = 0;           // packed statistics length
+  int64_t steps = 0;       // steps enqueued so far
+  std::vector<gplvm::ShardState> sh;
+};
+
+namespace gplvm {
+
+// dense.cu
+int dense_init_constants(gplvm_ppca_session* s);
+int dense_enqueue_step(gplvm_ppca_session* s);
+int dense_loglik(gplvm_ppca_session* s, double* ll);
+// dense_dmma.cu
+bool dense_dmma_eligible(const gplvm_ppca_session* s);
+int dense_dmma_prepare(gplvm_ppca_session* s);
+int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* A, const double* c);
+int dense_dmma_release(gplvm_ppca_session* s);
+int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
+// masked.cu
+int masked_init_constants(gplvm_ppca_session* s);
+int masked_enqueue_step(gplvm_ppca_session* s);
+int masked_loglik(gplvm_ppca_session* s, double* ll);
+int masked_restore(gplvm_ppca_session* s, double* restored, int64_t ld);
+// session.cu
+int session_allreduce_stats(gplvm_ppca_session* s, size_t count);
+int launch_reduce_partials(ShardState& sh, int64_t S, int nparts);
+
+// Generic split-K statistics GEMM shared by dense.cu and masked.cu (defined in dense.cu).
+// out block 1: rows [0,R1) x Q1 columns, block 2: rows [R1,R) x Q2 columns (Q2 <= Q1).
+enum RowKind { ROWS_DENSE = 0, ROWS_MASKED = 1 };
+int launch_stats_gemm(ShardState& sh, RowKind kind, int D, int R1, int R, int Q1, int Q2, const double* Cmat,
+                      int ldc, int Cw1, const double* Cmat2, int ldc2, int64_t S);
+
+}  // namespace gplvm

@@ -1,0 +1,454 @@
+// session.cu -- PPCA sessions: observation shards resident in HBM, host<->device movement in the
+// reference layout (Y is D x N feature-major; the device keeps observation-major rows so that one
+// observation is one contiguous, TMA-loadable row), the synthetic workload generator and the EM
+// driver implementing the reference stop rule (src/GPLVM/PPCA.hs:90-92, :173-181).
+#include "ppca.cuh"
+
+namespace gplvm {
+int moments_pass(gplvm_ppca_session* s, int mode);
+
+namespace {
+
+// out (cols x ld_out) <- in^T, in is (rows x ld_in); 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int64_t ld_in, double* __restrict__ out,
+                                                        int64_t ld_out, int64_t rows, int64_t cols) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j, c = c0 + tx;
+    t[j][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.0;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t c = c0 + j, r = r0 + tx;
+    if (c < cols && r < rows) out[c * ld_out + r] = t[tx][j];
+  }
+}
+
+// synthetic model of SURVEY.md 8(d): x_n = W_t z_n + mu_t + eps_n, all N(0,1); keyed by global n
+__global__ void __launch_bounds__(256) synth_kernel(double* __restrict__ X, int64_t ldx, int64_t n0, int64_t n_obs, int D,
+                                                    uint64_t seed, double nan_prob) {
+  constexpr int MT = 16;  // true latent dimension of the generator
+  __shared__ double zs[16][MT];
+  const int64_t base = (int64_t)blockIdx.x * 16;
+  {
+    const int o = threadIdx.x / MT, m = threadIdx.x % MT;
+    double z, u;
+    Philox::normal_uniform(seed ^ 0x5851F42D4C957F2DULL, (uint64_t)(n0 + base + o), (uint64_t)m, z, u);
+    zs[o][m] = z;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double wt[MT], mu, u;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) Philox::normal_uniform(seed ^ 0x14057B7EF767814FULL, (uint64_t)d, (uint64_t)m, wt[m], u);
+    Philox::normal_uniform(seed ^ 0x14057B7EF767814FULL, (uint64_t)d, (uint64_t)MT, mu, u);
+    for (int o = 0; o < 16; ++o) {
+      const int64_t n = base + o;
+      if (n >= n_obs) break;
+      double eps;
+      Philox::normal_uniform(seed, (uint64_t)(n0 + n), (uint64_t)d, eps, u);
+      double v = mu + eps;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) v = fma(wt[m], zs[o][m], v);
+      if (nan_prob > 0.0 && d != 0 && u < nan_prob) v = nan("");
+      X[n * ldx + d] = v;
+    }
+  }
+}
+
+__global__ void set_params_kernel(Par p, const double* __restrict__ W0, double sigma2_0) {
+  // W0 arrives as D x M (reference layout); pad to D x MP with zeros
+  for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < p.D * p.MP; e += blockDim.x * gridDim.x) {
+    const int d = e / p.MP, a = e % p.MP;
+    p.W[e] = (a < p.M) ? W0[(int64_t)d * p.M + a] : 0.0;
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int i = 0; i < S_COUNT; ++i)
+      if (i != S_TOTAL && i != S_KNOWN) p.scal[i] = 0.0;
+    p.scal[S_SIGMA2] = sigma2_0;
+  }
+}
+
+__global__ void set_scal_kernel(double* scal, int idx0, double v0, int idx1, double v1) {
+  scal[idx0] = v0;
+  if (idx1 >= 0) scal[idx1] = v1;
+}
+
+int64_t chunk_obs(int64_t D) {
+  int64_t c = ((int64_t)32 << 20) / (D > 0 ? D : 1);  // <= 256 MB staging
+  c = (c / 32) * 32;
+  if (c < 1024) c = 1024;
+  return c;
+}
+
+void free_shard(ShardState& sh) {
+  cudaSetDevice(sh.dev);
+  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.Av); cudaFree(sh.parblock); cudaFree(sh.stats);
+  cudaFree(sh.partials); cudaFree(sh.scratch);
+  if (sh.tmap) free(sh.tmap);
+  if (sh.ev0) cudaEventDestroy(sh.ev0);
+  if (sh.ev1) cudaEventDestroy(sh.ev1);
+  if (sh.evk0) cudaEventDestroy(sh.evk0);
+  if (sh.evk1) cudaEventDestroy(sh.evk1);
+  sh = ShardState();
+}
+
+}  // namespace
+
+int session_allreduce_stats(gplvm_ppca_session* s, size_t count) {
+  std::vector<double*> bufs;
+  for (ShardState& sh : s->sh) bufs.push_back(sh.stats);
+  return allreduce_sum(bufs, count);
+}
+
+static int check_async(gplvm_ppca_session* s, double* scal_out) {
+  // synchronise every shard and surface numeric failures
+  double scal[S_COUNT];
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    CUDA_TRY(cudaMemcpyAsync(scal, sh.par.scal, sizeof scal, cudaMemcpyDeviceToHost, sh.st));
+    CUDA_TRY(cudaStreamSynchronize(sh.st));
+    if (scal[S_ERR] != 0.0)
+      return fail(GPLVM_ERR_NUMERIC, "PPCA: a matrix that must be positive definite is not (step %lld)", (long long)scal[S_STEPS]);
+    if (&sh == &s->sh[0] && scal_out) memcpy(scal_out, scal, sizeof scal);
+  }
+  return GPLVM_OK;
+}
+
+}  // namespace gplvm
+
+using namespace gplvm;
+
+extern "C" {
+
+int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, int64_t obs_begin, int64_t obs_count,
+                         gplvm_ppca_session** out) {
+  if (!out) return fail(GPLVM_ERR_ARG, "session_create: null out");
+  *out = nullptr;
+  if (D < 1 || N_global < 1 || M < 1) return fail(GPLVM_ERR_ARG, "session_create: D, N, M must be positive");
+  if (M > GPLVM_MAX_M) return fail(GPLVM_ERR_ARG, "session_create: M = %lld exceeds GPLVM_MAX_M = %d", (long long)M, GPLVM_MAX_M);
+  if (D > (1 << 20)) return fail(GPLVM_ERR_ARG, "session_create: D too large");
+  if (obs_begin < 0 || obs_count < 1 || obs_begin + obs_count > N_global)
+    return fail(GPLVM_ERR_ARG, "session_create: observation block [%lld, +%lld) outside [0, %lld)", (long long)obs_begin,
+                (long long)obs_count, (long long)N_global);
+  GP_TRY(ensure_context());
+  Context& c = ctx();
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  if (!c.multiproc && (obs_begin != 0 || obs_count != N_global))
+    return fail(GPLVM_ERR_ARG, "session_create: partial observation blocks need gplvm_dist_init (multi-process mode)");
+  auto* s = new gplvm_ppca_session();
+  s->D = D; s->N = N_global; s->M = M; s->missing = missing != 0;
+  s->MP = s->missing ? (int)M : (int)round_up(M, 8);
+  if (s->MP > GPLVM_MAX_M) s->MP = GPLVM_MAX_M;
+  s->NV = s->MP * (s->MP + 1) / 2;
+  if (s->missing)  // S1 | G  (D x (M+NV)) ; S2 (D x M) ; sum ez (M)
+    s->S = D * (s->MP + s->NV) + (D + 1) * s->MP;
+  else             // XEz (D x MP) | EE (MP x MP) | sEz (MP)
+    s->S = (D + s->MP + 1) * s->MP;
+  const int nsh = (int)c.shards.size();
+  int used = nsh;
+  if (obs_count < used) used = (int)obs_count;
+  const int64_t per = ceil_div(obs_count, used);
+  s->sh.resize(used);
+  for (int i = 0; i < used; ++i) {
+    ShardState& sh = s->sh[i];
+    sh.dev = c.shards[i].device;
+    sh.st = c.shards[i].stream;
+    sh.n0 = obs_begin + per * i;
+    sh.n = std::min<int64_t>(per, obs_begin + obs_count - sh.n0);
+  }
+  if (used != nsh) {
+    delete s;
+    return fail(GPLVM_ERR_ARG, "session_create: fewer observations than GPUs");
+  }
+  s->use_dmma = dense_dmma_eligible(s);
+  const int MP = s->MP;
+  for (ShardState& sh : s->sh) {
+    cudaError_t e = cudaSetDevice(sh.dev);
+    sh.ldx = round_up(D, 4);
+    if (s->use_dmma) sh.ldx = D;
+    sh.nparts = 592;
+    if (s->use_dmma) sh.nparts = std::max(sh.nparts, dense_dmma_nparts(s, sh));
+    const size_t parlen = (size_t)D * MP * 3 + (size_t)MP * MP + MP + (size_t)D * 4 + S_COUNT + 64;
+    if (e == cudaSuccess) e = cudaMalloc(&sh.X, sizeof(double) * (size_t)sh.n * sh.ldx);
+    if (e == cudaSuccess && (s->missing || !s->use_dmma)) e = cudaMalloc(&sh.Ez, sizeof(double) * (size_t)sh.n * MP);
+    if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.Av, sizeof(double) * (size_t)sh.n * s->NV);
+    if (e == cudaSuccess) e = cudaMalloc(&sh.parblock, sizeof(double) * parlen);
+    if (e == cudaSuccess) e = cudaMemset(sh.parblock, 0, sizeof(double) * parlen);
+    if (e == cudaSuccess) e = cudaMalloc(&sh.stats, sizeof(double) * (size_t)std::max<int64_t>(s->S, 3 * D));
+    if (e == cudaSuccess) e = cudaMalloc(&sh.partials, sizeof(double) * (size_t)std::max<int64_t>(s->S, 3 * D) * sh.nparts);
+    if (e == cudaSuccess) e = cudaMalloc(&sh.scratch, sizeof(double) * (size_t)D * 8);
+    if (e == cudaSuccess) e = cudaEventCreate(&sh.ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&sh.ev1);
+    if (e != cudaSuccess) {
+      for (ShardState& t : s->sh) free_shard(t);
+      delete s;
+      return fail(GPLVM_ERR_CUDA, "session_create: allocation failed: %s", cudaGetErrorString(e));
+    }
+    double* q = sh.parblock;
+    Par& p = sh.par;
+    p.W = q; q += (size_t)D * MP;
+    p.A = q; q += (size_t)D * MP;
+    p.Wprev = q; q += (size_t)D * MP;
+    p.Minv = q; q += (size_t)MP * MP;
+    p.c = q; q += MP;
+    p.mu = q; q += D;
+    p.nd = q; q += D;
+    p.sy = q; q += D;
+    p.syy = q; q += D;
+    p.scal = q; q += S_COUNT;
+    p.D = (int)D; p.M = (int)M; p.MP = MP; p.NV = s->NV; p.N = N_global;
+  }
+  if (s->use_dmma) {
+    int rc = dense_dmma_prepare(s);
+    if (rc != GPLVM_OK) {
+      for (ShardState& t : s->sh) free_shard(t);
+      delete s;
+      return rc;
+    }
+  }
+  *out = s;
+  return GPLVM_OK;
+}
+
+int gplvm_session_destroy(gplvm_ppca_session* s) {
+  if (!s) return GPLVM_OK;
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  for (ShardState& sh : s->sh) {
+    cudaSetDevice(sh.dev);
+    cudaStreamSynchronize(sh.st);
+  }
+  dense_dmma_release(s);
+  for (ShardState& sh : s->sh) free_shard(sh);
+  delete s;
+  return GPLVM_OK;
+}
+
+int gplvm_session_load_host(gplvm_ppca_session* s, const double* Y, int64_t ld) {
+  if (!s || !Y) return fail(GPLVM_ERR_ARG, "session_load_host: null argument");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  const int64_t D = s->D;
+  const int64_t first = s->sh[0].n0;
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    const int64_t ch = std::min(chunk_obs(D), sh.n);
+    double* stage = nullptr;
+    CUDA_TRY(cudaMalloc(&stage, sizeof(double) * (size_t)D * ch));
+    for (int64_t c0 = 0; c0 < sh.n; c0 += ch) {
+      const int64_t cn = std::min(ch, sh.n - c0);
+      const double* src = Y + (sh.n0 - first) + c0;  // (feature 0, observation n0 + c0)
+      cudaError_t e = cudaMemcpy2DAsync(stage, sizeof(double) * ch, src, sizeof(double) * ld, sizeof(double) * cn, D,
+                                        cudaMemcpyHostToDevice, sh.st);
+      if (e != cudaSuccess) { cudaFree(stage); return fail(GPLVM_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+      dim3 grid((unsigned)ceil_div(cn, 32), (unsigned)ceil_div(D, 32));
+      GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, stage, ch, sh.X + c0 * sh.ldx, sh.ldx, D, cn);
+    }
+    CUDA_TRY(cudaStreamSynchronize(sh.st));
+    CUDA_TRY(cudaFree(stage));
+  }
+  s->has_data = true;
+  s->initialised = false;
+  return GPLVM_OK;
+}
+
+static int read_back(gplvm_ppca_session* s, bool restored, double* Yout, int64_t ld);
+
+int gplvm_session_read_data(gplvm_ppca_session* s, double* Y, int64_t ld) {
+  if (!s || !Y) return fail(GPLVM_ERR_ARG, "session_read_data: null argument");
+  if (!s->has_data) return fail(GPLVM_ERR_STATE, "session_read_data: no data loaded");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  const int64_t D = s->D, first = s->sh[0].n0;
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    const int64_t ch = std::min(chunk_obs(D), sh.n);
+    double* stage = nullptr;
+    CUDA_TRY(cudaMalloc(&stage, sizeof(double) * (size_t)D * ch));
+    for (int64_t c0 = 0; c0 < sh.n; c0 += ch) {
+      const int64_t cn = std::min(ch, sh.n - c0);
+      dim3 grid((unsigned)ceil_div(D, 32), (unsigned)ceil_div(cn, 32));
+      GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, sh.X + c0 * sh.ldx, sh.ldx, stage, ch, cn, D);
+      double* dst = Y + (sh.n0 - first) + c0;
+      cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * ld, stage, sizeof(double) * ch, sizeof(double) * cn, D,
+                                        cudaMemcpyDeviceToHost, sh.st);
+      if (e != cudaSuccess) { cudaFree(stage); return fail(GPLVM_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); }
+      CUDA_TRY(cudaStreamSynchronize(sh.st));
+    }
+    CUDA_TRY(cudaFree(stage));
+  }
+  return GPLVM_OK;
+}
+
+int gplvm_session_synth(gplvm_ppca_session* s, uint64_t seed, double nan_prob) {
+  if (!s) return fail(GPLVM_ERR_ARG, "session_synth: null session");
+  if (nan_prob > 0.0 && !s->missing) return fail(GPLVM_ERR_ARG, "session_synth: nan_prob > 0 needs a missing-data session");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(synth_kernel, (unsigned)ceil_div(sh.n, 16), 256, 0, sh.st, sh.X, sh.ldx, sh.n0, sh.n, (int)s->D, seed, nan_prob);
+  }
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    CUDA_TRY(cudaStreamSynchronize(sh.st));
+  }
+  s->has_data = true;
+  s->initialised = false;
+  return GPLVM_OK;
+}
+
+int gplvm_session_init(gplvm_ppca_session* s, const double* W0, double sigma2_0) {
+  if (!s || !W0) return fail(GPLVM_ERR_ARG, "session_init: null argument");
+  if (!s->has_data) return fail(GPLVM_ERR_STATE, "session_init: load or synthesise data first");
+  if (!(sigma2_0 > 0.0)) return fail(GPLVM_ERR_ARG, "session_init: sigma2_0 must be positive");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    double* w0d = sh.par.Wprev;  // staging for the D x M host matrix
+    CUDA_TRY(cudaMemcpyAsync(w0d, W0, sizeof(double) * s->D * s->M, cudaMemcpyHostToDevice, sh.st));
+    GP_LAUNCH(set_params_kernel, 8, 256, 0, sh.st, sh.par, w0d, sigma2_0);
+  }
+  s->steps = 0;
+  GP_TRY(s->missing ? masked_init_constants(s) : dense_init_constants(s));
+  GP_TRY(check_async(s, nullptr));
+  s->initialised = true;
+  return GPLVM_OK;
+}
+
+int gplvm_session_steps(gplvm_ppca_session* s, int64_t steps) {
+  if (!s) return fail(GPLVM_ERR_ARG, "session_steps: null session");
+  if (!s->initialised) return fail(GPLVM_ERR_STATE, "session_steps: call gplvm_session_init first");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    CUDA_TRY(cudaEventRecord(sh.ev0, sh.st));
+  }
+  for (int64_t i = 0; i < steps; ++i) GP_TRY(s->missing ? masked_enqueue_step(s) : dense_enqueue_step(s));
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    CUDA_TRY(cudaEventRecord(sh.ev1, sh.st));
+  }
+  s->steps += steps;
+  return GPLVM_OK;
+}
+
+int gplvm_session_sync(gplvm_ppca_session* s) {
+  if (!s) return fail(GPLVM_ERR_ARG, "session_sync: null session");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  return check_async(s, nullptr);
+}
+
+int gplvm_session_run(gplvm_ppca_session* s, int stop_kind, int64_t k, double tol, int64_t* steps_done) {
+  if (!s) return fail(GPLVM_ERR_ARG, "session_run: null session");
+  if (!s->initialised) return fail(GPLVM_ERR_STATE, "session_run: call gplvm_session_init first");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  double scal[S_COUNT];
+  if (stop_kind == GPLVM_STOP_ITERATIONS) {
+    // Left k: continue while k > iteration, iteration starting at 0  =>  max(k,0)+1 steps (PPCA.hs:91)
+    const int64_t total = (k > 0 ? k : 0) + 1;
+    GP_TRY(gplvm_session_steps(s, total));
+    GP_TRY(check_async(s, scal));
+  } else if (stop_kind == GPLVM_STOP_TOLERANCE) {
+    // Right tol: the update kernel raises DONE once max(|ds2|, max|dW|) <= tol; later steps are no-ops.
+    for (ShardState& sh : s->sh) {
+      CUDA_TRY(cudaSetDevice(sh.dev));
+      GP_LAUNCH(set_scal_kernel, 1, 1, 0, sh.st, sh.par.scal, (int)S_TOL, tol, (int)S_USETOL, 1.0);
+    }
+    const int64_t cap = (int64_t)1 << 40;
+    int64_t batch = 4;
+    for (int64_t done = 0; done < cap;) {
+      GP_TRY(gplvm_session_steps(s, batch));
+      done += batch;
+      GP_TRY(check_async(s, scal));
+      if (scal[S_DONE] != 0.0) break;
+      if (batch < 64) batch *= 2;
+    }
+    for (ShardState& sh : s->sh) {
+      CUDA_TRY(cudaSetDevice(sh.dev));
+      GP_LAUNCH(set_scal_kernel, 1, 1, 0, sh.st, sh.par.scal, (int)S_USETOL, 0.0, (int)S_DONE, 0.0);
+    }
+    GP_TRY(check_async(s, nullptr));
+  } else {
+    return fail(GPLVM_ERR_ARG, "session_run: unknown stop_kind %d", stop_kind);
+  }
+  s->steps = (int64_t)scal[S_STEPS];
+  if (steps_done) *steps_done = (int64_t)scal[S_STEPS];
+  return GPLVM_OK;
+}
+
+int gplvm_session_params(gplvm_ppca_session* s, double* W, double* sigma2, double* mu, double* dsigma2, double* max_dw,
+                         int64_t* steps_done) {
+  if (!s) return fail(GPLVM_ERR_ARG, "session_params: null session");
+  if (!s->initialised) return fail(GPLVM_ERR_STATE, "session_params: not initialised");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  double scal[S_COUNT];
+  GP_TRY(check_async(s, scal));
+  ShardState& sh = s->sh[0];
+  CUDA_TRY(cudaSetDevice(sh.dev));
+  if (W) {
+    std::vector<double> tmp((size_t)s->D * s->MP);
+    CUDA_TRY(cudaMemcpy(tmp.data(), sh.par.W, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (int64_t d = 0; d < s->D; ++d)
+      for (int64_t a = 0; a < s->M; ++a) W[d * s->M + a] = tmp[d * s->MP + a];
+  }
+  if (mu) CUDA_TRY(cudaMemcpy(mu, sh.par.mu, sizeof(double) * s->D, cudaMemcpyDeviceToHost));
+  if (sigma2) *sigma2 = scal[S_SIGMA2];
+  if (dsigma2) *dsigma2 = scal[S_DVAR];
+  if (max_dw) *max_dw = scal[S_MAXDW];
+  if (steps_done) *steps_done = (int64_t)scal[S_STEPS];
+  return GPLVM_OK;
+}
+
+int gplvm_session_loglik(gplvm_ppca_session* s, double* loglik_out) {
+  if (!s || !loglik_out) return fail(GPLVM_ERR_ARG, "session_loglik: null argument");
+  if (!s->initialised) return fail(GPLVM_ERR_STATE, "session_loglik: not initialised");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  return s->missing ? masked_loglik(s, loglik_out) : dense_loglik(s, loglik_out);
+}
+
+int gplvm_session_restored(gplvm_ppca_session* s, double* restored, int64_t ld) {
+  if (!s || !restored) return fail(GPLVM_ERR_ARG, "session_restored: null argument");
+  if (!s->missing) return fail(GPLVM_ERR_STATE, "session_restored: dense sessions have no restored matrix (Nothing, PPCA.hs:91)");
+  if (!s->initialised || s->steps < 1) return fail(GPLVM_ERR_STATE, "session_restored: run at least one EM step first");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  return masked_restore(s, restored, ld);
+}
+
+int gplvm_session_set_kernel_timing(gplvm_ppca_session* s, int on) {
+  if (!s) return fail(GPLVM_ERR_ARG, "null session");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    if (on && !sh.evk0) {
+      CUDA_TRY(cudaEventCreate(&sh.evk0));
+      CUDA_TRY(cudaEventCreate(&sh.evk1));
+    } else if (!on && sh.evk0) {
+      cudaEventDestroy(sh.evk0); cudaEventDestroy(sh.evk1);
+      sh.evk0 = sh.evk1 = nullptr;
+    }
+  }
+  return GPLVM_OK;
+}
+
+int gplvm_session_last_steps_ms(gplvm_ppca_session* s, double* total_ms, double* kernel_ms) {
+  if (!s) return fail(GPLVM_ERR_ARG, "null session");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  double tmax = 0.0, kmax = 0.0;
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    CUDA_TRY(cudaEventSynchronize(sh.ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, sh.ev0, sh.ev1));
+    if (ms > tmax) tmax = ms;
+    if (sh.evk0) {
+      // events bracket the statistics pass of the LAST step of the batch
+      CUDA_TRY(cudaEventElapsedTime(&ms, sh.evk0, sh.evk1));
+      if (ms > kmax) kmax = ms;
+    }
+  }
+  if (total_ms) *total_ms = tmax;
+  if (kernel_ms) *kernel_ms = kmax;
+  return GPLVM_OK;
+}
+
+}  // extern "C"
