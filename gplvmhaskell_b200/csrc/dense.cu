@@ -214,7 +214,7 @@ __device__ void dense_prep_block(const Par& p, double* sm) {
     double ld = 0.0;
     for (int i = 0; i < M; ++i) ld += log(Mm[i * MP + i]);
     p.scal[S_LOGDETM] = 2.0 * ld;
-    if (!ok) p.scal[S_ERR] = 1.0;
+    if (!ok) set_err(p.scal, 1.0);
   }
   block_chol_inverse(Mm, Mi, MP, MP);
   for (int e = threadIdx.x; e < MP * MP; e += blockDim.x) p.Minv[e] = Mi[e];
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(Par p, const double* 
     p.scal[S_DVAR] = dvar;
     p.scal[S_MAXDW] = maxdw;
     p.scal[S_STEPS] += 1.0;
-    if (!ok || !(news2 > 0.0)) p.scal[S_ERR] = 1.0;
+    if (!ok || !(news2 > 0.0)) set_err(p.scal, 1.0);
     if (p.scal[S_USETOL] != 0.0 && !(fmax(dvar, maxdw) > p.scal[S_TOL])) p.scal[S_DONE] = 1.0;
   }
   __syncthreads();

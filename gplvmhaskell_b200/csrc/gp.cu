@@ -1,0 +1,572 @@
+// gp.cu -- GP kernel-matrix build fused with a blocked, tiled FP64 Cholesky, log-determinant and the
+// log marginal likelihood; plus the stand-alone kernel builder, Cholesky and lower-triangular solve.
+//
+// Reference call sites (all relative to the reference checkout):
+//   src/GPLVM/GPExample.hs:79-91     sqDist          (expanded square, result is len(v2) x len(v1))
+//   src/GPLVM/GPExample.hs:93-100    kernelFunction  (exp(-0.5 * (1/0.1) * d2))
+//   src/GPLVM/GaussianProcess.hs:67-68  cholSH (K + 5e-5 I)
+//   src/GPLVM/GaussianProcess.hs:74,77  linearSolveS cholK ...   (triangular factor solves)
+// Extension (BASELINE.json north_star / SURVEY.md 8a row G4): Q-dimensional ARD inputs and
+//   lml = -1/2 |L^-1 y|^2 - sum log L_ii - N/2 log 2 pi.
+//
+// Factorisation layout: the matrix lives in HBM as N x N row-major, lower triangle only is touched.
+// Right-looking blocked algorithm with panel width NB = 128:
+//   panel k:  [diag]  L11 = chol(A11) in shared memory by one CTA, T = L11^-1 (triangular inverse),
+//                     alpha_k = T y_k, logdet += 2 sum log diag(L11)
+//             [panel] L21 = A21 T^T            (FP64 tensor-core GEMM, C = A B^T form), fused with the
+//                     forward-substitution update y_rest -= L21 alpha_k
+//             [syrk]  A22 -= L21 L21^T         (same GEMM kernel, lower tiles only).  For k = 0 the
+//                     epilogue GENERATES the kernel-matrix tile instead of reading it, so the N x N kernel
+//                     matrix is never written to and re-read from HBM before the factorisation
+//                     touches it ("kernel build fused with the Cholesky").
+// The GEMM uses mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 on sm_100a; tcgen05 has no FP64 kind).
+#include "common.cuh"
+
+namespace gplvm {
+namespace {
+
+constexpr int NB = 128;      // panel width == GEMM tile edge
+constexpr int KC = 16;       // K chunk staged in shared memory
+constexpr int KP = KC + 4;   // padded row stride (doubles) of a staged chunk: conflict-free fragment loads
+constexpr int STAGES = 3;
+constexpr int GEMM_SMEM = STAGES * 2 * NB * KP * (int)sizeof(double);
+
+struct KernelSpec {      // how to generate a kernel-matrix entry on the fly
+  const double* X;       // N x Q row-major inputs (device)
+  const double* inv_l2;  // Q
+  double variance, jitter;
+  int Q;
+};
+
+// variance * exp(-0.5 * sum_q inv_l2[q] * (a_q^2 + (b_q^2 - 2 a_q b_q)))  -- the association order of
+// sqDist (GPExample.hs:83-87): v1^2 + (v2^2 - 2 v1 v2), with a = X1[i], b = X2[j].
+__device__ __forceinline__ double rbf_entry(const double* __restrict__ a, const double* __restrict__ b,
+                                            const double* __restrict__ inv_l2, int Q, double variance) {
+  double acc = 0.0;
+  for (int q = 0; q < Q; ++q) {
+    const double v1 = a[q], v2 = b[q];
+    const double d2 = __dadd_rn(__dmul_rn(v1, v1), __dsub_rn(__dmul_rn(v2, v2), __dmul_rn(__dmul_rn(2.0, v1), v2)));
+    acc = __dadd_rn(acc, __dmul_rn(inv_l2[q], d2));
+  }
+  return variance * exp(-0.5 * acc);
+}
+
+// K_out[j * n1 + i] = k(X1[i], X2[j]); i is the fastest index => coalesced, 2 entries per thread.
+__global__ void __launch_bounds__(256) rbf_build_kernel(const double* __restrict__ X1, int64_t n1, const double* __restrict__ X2,
+                                                        int64_t n2, int Q, const double* __restrict__ inv_l2, double variance,
+                                                        double* __restrict__ out, int64_t ldo, int64_t j_begin, int64_t j_count) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int64_t j = j_begin + blockIdx.y;
+  if (i >= n1 || j >= j_begin + j_count) return;
+  const double* b = X2 + j * Q;
+  const double v0 = rbf_entry(X1 + i * Q, b, inv_l2, Q, variance);
+  if (i + 1 < n1) {
+    const double v1 = rbf_entry(X1 + (i + 1) * Q, b, inv_l2, Q, variance);
+    if (((ldo | i) & 1) == 0) {
+      *reinterpret_cast<double2*>(out + (j - j_begin) * ldo + i) = make_double2(v0, v1);
+    } else {
+      out[(j - j_begin) * ldo + i] = v0;
+      out[(j - j_begin) * ldo + i + 1] = v1;
+    }
+  } else {
+    out[(j - j_begin) * ldo + i] = v0;
+  }
+}
+
+// first panel of the fused factorisation: A[i][j] for j < nb, i >= j (row-major, ld = N), with jitter
+__global__ void __launch_bounds__(128) gp_first_panel_kernel(double* __restrict__ A, int64_t ld, int nb, KernelSpec ks) {
+  const int64_t i = blockIdx.x;
+  const int j = threadIdx.x;
+  if (j >= nb || j > i) return;
+  double v = rbf_entry(ks.X + (int64_t)j * ks.Q, ks.X + i * ks.Q, ks.inv_l2, ks.Q, ks.variance);
+  if (i == j) v += ks.jitter;
+  A[i * ld + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagonal block: Cholesky + triangular inverse + forward-substitution piece + log-determinant
+// ------------------------------------------------------------------------------------------------
+// state[0] = sum log diag(L) so far, state[1] = error flag (index of the failing panel + 1)
+//
+// Shared tile Ls (nb x LDS): lower triangle = L; after the factorisation the strict upper triangle receives the
+// strictly-lower part of T = L^-1 TRANSPOSED (T[i][j], i > j, lives at Ls[j][i]); diag(T) = 1 / diag(L).
+constexpr int LDS_DIAG = NB + 1;
+constexpr int DIAG_SMEM = NB * LDS_DIAG * (int)sizeof(double);
+
+// T = L^-1 by forward substitution on e_j, one thread per column j (reads row j of the upper triangle as
+// its own history => bank-conflict free, stride LDS_DIAG between threads).
+__device__ __forceinline__ void tri_inverse_in_place(double* Ls, int nb) {
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    const double tjj = 1.0 / Ls[j * LDS_DIAG + j];
+    for (int i = j + 1; i < nb; ++i) {
+      double s = -Ls[i * LDS_DIAG + j] * tjj;
+      for (int k = j + 1; k < i; ++k) s = fma(-Ls[i * LDS_DIAG + k], Ls[j * LDS_DIAG + k], s);
+      Ls[j * LDS_DIAG + i] = s / Ls[i * LDS_DIAG + i];
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ double tinv_at(const double* Ls, int i, int j) {
+  return (j < i) ? Ls[j * LDS_DIAG + i] : ((i == j) ? 1.0 / Ls[i * LDS_DIAG + i] : 0.0);
+}
+
+__global__ void __launch_bounds__(256) gp_diag_kernel(double* __restrict__ A, int64_t ld, int64_t k0, int nb, double* __restrict__ Tinv,
+                                                      double* __restrict__ y, double* __restrict__ alpha, double* __restrict__ state) {
+  extern __shared__ double sm[];
+  double* Ls = sm;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < nb * nb; e += blockDim.x) {
+    const int i = e / nb, j = e % nb;
+    Ls[i * LDS_DIAG + j] = (j <= i) ? A[(k0 + i) * ld + (k0 + j)] : 0.0;
+  }
+  __syncthreads();
+  const bool ok = block_cholesky(Ls, nb, LDS_DIAG);
+  for (int e = tid; e < nb * nb; e += blockDim.x) {
+    const int i = e / nb, j = e % nb;
+    if (j <= i) A[(k0 + i) * ld + (k0 + j)] = Ls[i * LDS_DIAG + j];
+  }
+  __syncthreads();
+  tri_inverse_in_place(Ls, nb);
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int i = e / NB, j = e % NB;
+    Tinv[e] = (i < nb && j < nb) ? tinv_at(Ls, i, j) : 0.0;
+  }
+  if (y) {
+    for (int i = tid; i < nb; i += blockDim.x) {
+      double s = 0.0;
+      for (int k = 0; k <= i; ++k) s = fma(tinv_at(Ls, i, k), y[k0 + k], s);
+      alpha[k0 + i] = s;
+    }
+  }
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < nb; ++i) s += log(Ls[i * LDS_DIAG + i]);
+    state[0] += s;
+    if (!ok && state[1] == 0.0) state[1] = (double)(k0 / NB + 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-core GEMM, C(128 x 128 tile) = op(C) - / = A(rows i) . B(rows j)^T over K
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 16 : 0;  // zero-fill when predicated off
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+enum GemmMode { MODE_PANEL = 0, MODE_SYRK = 1, MODE_SYRK_GEN = 2 };
+
+// MODE_PANEL : rows [r0, N) of the panel: C = A . B^T, A = C's own panel columns (in place), B = Tinv (NB x NB);
+//              one CTA per 128-row strip; also y[i] -= sum_j C[i][j] alpha[j].
+// MODE_SYRK  : trailing matrix, lower tiles: C -= A . B^T with A = panel rows of tile-row, B = panel rows of tile-col.
+// MODE_SYRK_GEN: as SYRK but C is generated from the kernel function instead of being read.
+// All row indices are global; `Kdim` = panel width actually used (multiple of 4, <= NB); A/B rows have leading dim lda/ldb.
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) gp_gemm_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ Apan, int64_t lda,
+                                                        const double* __restrict__ Bmat, int64_t ldb, int64_t r0, int64_t N,
+                                                        int64_t ccol0, int Kdim, double* __restrict__ y,
+                                                        const double* __restrict__ alpha, KernelSpec ks) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps; warp tile 64 x 32
+
+  int64_t ti, tj;  // tile row / col (units of NB) relative to r0
+  if (MODE == MODE_PANEL) {
+    ti = blockIdx.x; tj = 0;
+  } else {
+    // triangular index: blockIdx.x = ti (ti + 1) / 2 + tj, tj <= ti
+    const int64_t b = blockIdx.x;
+    ti = (int64_t)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
+    while (ti * (ti + 1) / 2 > b) --ti;
+    tj = b - ti * (ti + 1) / 2;
+  }
+  const int64_t row0 = r0 + ti * NB;                                   // first global row of the C tile
+  const int64_t brow0 = (MODE == MODE_PANEL) ? 0 : r0 + tj * NB;      // first row of the B operand
+  const int64_t col0 = (MODE == MODE_PANEL) ? ccol0 : r0 + tj * NB;   // first global column of the C tile
+  const int64_t brows = (MODE == MODE_PANEL) ? NB : N;                // rows available in B
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nchunks = (Kdim + KC - 1) / KC;
+  auto load_chunk = [&](int c, int stage) {
+    double* As = smem + (size_t)stage * 2 * NB * KP;
+    double* Bs = As + NB * KP;
+    const int kc0 = c * KC;
+    // 128 rows x 16 doubles = 128 x 8 16-byte pieces per operand; 256 threads -> 4 pieces each per operand
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = tid + it * 256;
+      const int r = e >> 3, p = e & 7;
+      const int kk = kc0 + p * 2;
+      const bool kin = kk < Kdim;
+      const int64_t ar = row0 + r;
+      const bool pa = kin && ar < N;
+      cp_async16(As + r * KP + p * 2, Apan + (pa ? ar * lda + kk : 0), pa);
+      const int64_t br = brow0 + r;
+      const bool pb = kin && br < brows;
+      cp_async16(Bs + r * KP + p * 2, Bmat + (pb ? br * ldb + kk : 0), pb);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nchunks) load_chunk(s, s);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int cn = c + STAGES - 1;
+      if (cn < nchunks) load_chunk(cn, cn % STAGES);
+      cp_async_commit();
+    }
+    const double* As = smem + (size_t)(c % STAGES) * 2 * NB * KP;
+    const double* Bs = As + NB * KP;
+#pragma unroll
+    for (int k4 = 0; k4 < KC; k4 += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = As[(wm * 64 + i * 8 + g) * KP + k4 + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[(wn * 32 + j * 8 + g) * KP + k4 + t];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // every warp is done reading the staged operands (PANEL writes C == A in place)
+
+  // epilogue: thread owns C[row0 + wm*64 + i*8 + g][col0 + wn*32 + j*8 + 2t + {0,1}]
+  double ydot[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ydot[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + wm * 64 + i * 8 + g;
+    if (r >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int lc = wn * 32 + j * 8 + 2 * t;
+      const int64_t cc = col0 + lc;
+      if (MODE == MODE_PANEL) {
+        if (lc < Kdim) {
+          double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+          *reinterpret_cast<double2*>(C + r * ldc + cc) = v;
+          if (alpha) ydot[i] = fma(v.x, alpha[cc], fma(v.y, alpha[cc + 1], ydot[i]));
+        }
+      } else {
+        if (cc > r) continue;  // strictly upper part of a diagonal tile (cc even, so cc+1 > r handled below)
+        double2 v;
+        if (MODE == MODE_SYRK_GEN) {
+          v.x = rbf_entry(ks.X + cc * ks.Q, ks.X + r * ks.Q, ks.inv_l2, ks.Q, ks.variance);
+          v.y = (cc + 1 <= r) ? rbf_entry(ks.X + (cc + 1) * ks.Q, ks.X + r * ks.Q, ks.inv_l2, ks.Q, ks.variance) : 0.0;
+          if (cc == r) v.x += ks.jitter;
+          if (cc + 1 == r) v.y += ks.jitter;
+        } else {
+          v = *reinterpret_cast<const double2*>(C + r * ldc + cc);
+        }
+        v.x -= acc[i][j][0];
+        v.y -= acc[i][j][1];
+        if (cc + 1 <= r) *reinterpret_cast<double2*>(C + r * ldc + cc) = v;
+        else C[r * ldc + cc] = v.x;
+      }
+    }
+  }
+  if (MODE == MODE_PANEL && alpha) {
+    // y[r] -= sum over the 4 column-warps and the 4 lanes of a quad: shared-memory reduction, fixed order
+    double* red = smem;  // 128 rows x 16 partial sums (4 wn x 4 t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[(wm * 64 + i * 8 + g) * 16 + wn * 4 + t] = ydot[i];
+    __syncthreads();
+    if (tid < NB) {
+      const int64_t r = row0 + tid;
+      if (r < N) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) s += red[tid * 16 + q];
+        y[r] -= s;
+      }
+    }
+  }
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ A, int64_t N, int64_t ld) {
+  const int64_t i = blockIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N && j > i) A[i * ld + j] = 0.0;
+}
+
+__global__ void gp_lml_kernel(const double* __restrict__ alpha, int64_t N, double* __restrict__ state) {
+  __shared__ double red[40];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) s = fma(alpha[i], alpha[i], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    state[2] = s;                                                                 // |L^-1 y|^2
+    state[3] = -0.5 * s - state[0] - 0.5 * (double)N * log(2.0 * M_PI);           // lml
+  }
+}
+
+// X (n x R) <- Tinv (n x n used) . B_k ; then B_rest -= L21 X_k : simple CUDA-core kernels (the GP posterior
+// path, GaussianProcess.hs:74,77, is a "next" row of SURVEY.md 8f; these keep gplvm_tri_solve_lower correct).
+__global__ void __launch_bounds__(256) tri_diag_apply_kernel(const double* __restrict__ Tinv, int nb, const double* __restrict__ B,
+                                                             double* __restrict__ Xo, int64_t R, int64_t k0) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  for (int i = 0; i < nb; ++i) {
+    double s = 0.0;
+    for (int k = 0; k <= i; ++k) s = fma(Tinv[i * NB + k], B[(k0 + k) * R + r], s);
+    Xo[(k0 + i) * R + r] = s;
+  }
+}
+__global__ void __launch_bounds__(256) tri_update_kernel(const double* __restrict__ L, int64_t ld, int64_t N, int64_t k0, int nb,
+                                                         const double* __restrict__ Xo, double* __restrict__ B, int64_t R) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = k0 + nb + blockIdx.y;
+  if (r >= R || i >= N) return;
+  double s = 0.0;
+  for (int k = 0; k < nb; ++k) s = fma(L[i * ld + k0 + k], Xo[(k0 + k) * R + r], s);
+  B[i * R + r] -= s;
+}
+__global__ void __launch_bounds__(256) tri_inverse_kernel(const double* __restrict__ L, int64_t ld, int64_t k0, int nb,
+                                                          double* __restrict__ Tinv, double* __restrict__ state) {
+  extern __shared__ double sm[];
+  double* Ls = sm;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < nb * nb; e += blockDim.x) {
+    const int i = e / nb, j = e % nb;
+    Ls[i * LDS_DIAG + j] = (j <= i) ? L[(k0 + i) * ld + (k0 + j)] : 0.0;
+  }
+  __syncthreads();
+  for (int j = tid; j < nb; j += blockDim.x)
+    if (Ls[j * LDS_DIAG + j] == 0.0) state[1] = 1.0;
+  tri_inverse_in_place(Ls, nb);
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int i = e / NB, j = e % NB;
+    Tinv[e] = (i < nb && j < nb) ? tinv_at(Ls, i, j) : 0.0;
+  }
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+int set_gemm_attrs() {
+  static bool done = false;
+  if (done) return GPLVM_OK;
+  CUDA_TRY(cudaFuncSetAttribute(gp_gemm_kernel<MODE_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(gp_gemm_kernel<MODE_SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(gp_gemm_kernel<MODE_SYRK_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  const int diag_smem = DIAG_SMEM;
+  CUDA_TRY(cudaFuncSetAttribute(gp_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+  CUDA_TRY(cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+  done = true;
+  return GPLVM_OK;
+}
+
+// Factorise the N x N matrix in dA (row-major, lower part) in place.  gen != nullptr: the matrix is the
+// kernel matrix of gen->X and is generated on the fly (dA's lower part is written, never read before).
+// dy (nullable): right-hand side overwritten by the forward substitution; dalpha receives L^-1 y.
+int factorise(double* dA, int64_t N, int64_t ld, const KernelSpec* gen, double* dy, double* dalpha, double* dTinv, double* dstate,
+              cudaStream_t st) {
+  GP_TRY(set_gemm_attrs());
+  const int diag_smem = DIAG_SMEM;
+  KernelSpec ks{};
+  if (gen) ks = *gen;
+  if (gen) {
+    const int nb0 = (int)std::min<int64_t>(NB, N);
+    GP_LAUNCH(gp_first_panel_kernel, (unsigned)N, 128, 0, st, dA, ld, nb0, ks);
+  }
+  for (int64_t k0 = 0; k0 < N; k0 += NB) {
+    const int nb = (int)std::min<int64_t>(NB, N - k0);
+    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, st, dA, ld, k0, nb, dTinv, dy, dalpha, dstate);
+    const int64_t r0 = k0 + nb;
+    if (r0 >= N) break;
+    const int64_t T = ceil_div(N - r0, NB);
+    const int Kdim = (int)round_up(nb, 4);  // nb == NB here except for the last (incomplete) panel, which has no rows below
+    GP_LAUNCH(gp_gemm_kernel<MODE_PANEL>, (unsigned)T, 256, GEMM_SMEM, st, dA, ld, dA + k0, ld, dTinv, (int64_t)NB, r0, N, k0, Kdim,
+              dy, dy ? dalpha : nullptr, ks);
+    const int64_t ntiles = T * (T + 1) / 2;
+    if (gen && k0 == 0)
+      GP_LAUNCH(gp_gemm_kernel<MODE_SYRK_GEN>, (unsigned)ntiles, 256, GEMM_SMEM, st, dA, ld, dA + k0, ld, dA + k0, ld, r0, N, 0, Kdim,
+                nullptr, nullptr, ks);
+    else
+      GP_LAUNCH(gp_gemm_kernel<MODE_SYRK>, (unsigned)ntiles, 256, GEMM_SMEM, st, dA, ld, dA + k0, ld, dA + k0, ld, r0, N, 0, Kdim,
+                nullptr, nullptr, ks);
+  }
+  return GPLVM_OK;
+}
+
+int copy_lower_to_host(double* dA, int64_t N, int64_t ld, double* L_out, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)N);
+  GP_LAUNCH(zero_upper_kernel, grid, 256, 0, st, dA, N, ld);
+  CUDA_TRY(cudaMemcpy2DAsync(L_out, sizeof(double) * N, dA, sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return GPLVM_OK;
+}
+
+}  // namespace
+}  // namespace gplvm
+
+using namespace gplvm;
+
+extern "C" {
+
+int gplvm_rbf_kernel(const double* X1, int64_t n1, const double* X2, int64_t n2, int64_t Q, const double* inv_lengthscale2,
+                     double variance, double* K_out) {
+  if (!X1 || !X2 || !inv_lengthscale2 || !K_out) return fail(GPLVM_ERR_ARG, "gplvm_rbf_kernel: null argument");
+  if (n1 < 1 || n2 < 1 || Q < 1 || Q > 64) return fail(GPLVM_ERR_ARG, "gplvm_rbf_kernel: sizes must be positive (Q <= 64)");
+  GP_TRY(ensure_context());
+  Context& c = ctx();
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  CUDA_TRY(cudaSetDevice(c.shards[0].device));
+  cudaStream_t st = c.shards[0].stream;
+  DevBuf d1, d2, dl, dk;
+  // rows of K_out are produced in chunks so that any n2 x n1 fits next to the inputs
+  const int64_t rows_per_chunk = std::max<int64_t>(1, std::min<int64_t>(n2, ((int64_t)1 << 28) / n1));
+  CUDA_TRY(cudaMalloc(&d1.p, sizeof(double) * n1 * Q));
+  CUDA_TRY(cudaMalloc(&d2.p, sizeof(double) * n2 * Q));
+  CUDA_TRY(cudaMalloc(&dl.p, sizeof(double) * Q));
+  CUDA_TRY(cudaMalloc(&dk.p, sizeof(double) * rows_per_chunk * n1));
+  CUDA_TRY(cudaMemcpyAsync(d1.p, X1, sizeof(double) * n1 * Q, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d2.p, X2, sizeof(double) * n2 * Q, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dl.p, inv_lengthscale2, sizeof(double) * Q, cudaMemcpyHostToDevice, st));
+  for (int64_t j0 = 0; j0 < n2; j0 += rows_per_chunk) {
+    const int64_t jc = std::min(rows_per_chunk, n2 - j0);
+    for (int64_t jj = 0; jj < jc; jj += 32768) {  // grid.y limit
+      const int64_t jn = std::min<int64_t>(32768, jc - jj);
+      dim3 grid((unsigned)ceil_div(n1, 512), (unsigned)jn);
+      GP_LAUNCH(rbf_build_kernel, grid, 256, 0, st, d1.as<double>(), n1, d2.as<double>(), n2, (int)Q, dl.as<double>(), variance,
+                dk.as<double>() + jj * n1, n1, j0 + jj, jn);
+    }
+    CUDA_TRY(cudaMemcpyAsync(K_out + j0 * n1, dk.p, sizeof(double) * jc * n1, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GPLVM_OK;
+}
+
+int gplvm_gp_chol_lml(const double* X, int64_t N, int64_t Q, const double* y, const double* inv_lengthscale2, double variance,
+                      double jitter, double* L_out, double* lml_out, double* logdet_out) {
+  if (!X || !inv_lengthscale2) return fail(GPLVM_ERR_ARG, "gplvm_gp_chol_lml: null argument");
+  if (N < 1 || Q < 1 || Q > 64) return fail(GPLVM_ERR_ARG, "gplvm_gp_chol_lml: sizes must be positive (Q <= 64)");
+  if (lml_out && !y) return fail(GPLVM_ERR_ARG, "gplvm_gp_chol_lml: y is required for the log marginal likelihood");
+  GP_TRY(ensure_context());
+  Context& c = ctx();
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  CUDA_TRY(cudaSetDevice(c.shards[0].device));
+  cudaStream_t st = c.shards[0].stream;
+  DevBuf dX, dl, dA, dy, dal, dT, dst;
+  const int64_t ld = round_up(N, 2);  // 16-byte aligned rows for the staged copies
+  CUDA_TRY(cudaMalloc(&dX.p, sizeof(double) * N * Q));
+  CUDA_TRY(cudaMalloc(&dl.p, sizeof(double) * Q));
+  CUDA_TRY(cudaMalloc(&dA.p, sizeof(double) * (size_t)N * ld));
+  CUDA_TRY(cudaMalloc(&dy.p, sizeof(double) * N));
+  CUDA_TRY(cudaMalloc(&dal.p, sizeof(double) * N));
+  CUDA_TRY(cudaMalloc(&dT.p, sizeof(double) * NB * NB));
+  CUDA_TRY(cudaMalloc(&dst.p, sizeof(double) * 8));
+  CUDA_TRY(cudaMemsetAsync(dst.p, 0, sizeof(double) * 8, st));
+  CUDA_TRY(cudaMemcpyAsync(dX.p, X, sizeof(double) * N * Q, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dl.p, inv_lengthscale2, sizeof(double) * Q, cudaMemcpyHostToDevice, st));
+  if (y) CUDA_TRY(cudaMemcpyAsync(dy.p, y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+  KernelSpec ks{dX.as<double>(), dl.as<double>(), variance, jitter, (int)Q};
+  GP_TRY(factorise(dA.as<double>(), N, ld, &ks, y ? dy.as<double>() : nullptr, dal.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  if (y) GP_LAUNCH(gp_lml_kernel, 1, 256, 0, st, dal.as<double>(), N, dst.as<double>());
+  double state[8];
+  CUDA_TRY(cudaMemcpyAsync(state, dst.p, sizeof state, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (state[1] != 0.0)
+    return fail(GPLVM_ERR_NUMERIC, "gplvm_gp_chol_lml: kernel matrix not positive definite (panel %d)", (int)state[1] - 1);
+  if (lml_out) *lml_out = state[3];
+  if (logdet_out) *logdet_out = 2.0 * state[0];
+  if (L_out) GP_TRY(copy_lower_to_host(dA.as<double>(), N, ld, L_out, st));
+  return GPLVM_OK;
+}
+
+int gplvm_cholesky(const double* A, int64_t N, double* L_out) {
+  if (!A || !L_out) return fail(GPLVM_ERR_ARG, "gplvm_cholesky: null argument");
+  if (N < 1) return fail(GPLVM_ERR_ARG, "gplvm_cholesky: N must be positive");
+  GP_TRY(ensure_context());
+  Context& c = ctx();
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  CUDA_TRY(cudaSetDevice(c.shards[0].device));
+  cudaStream_t st = c.shards[0].stream;
+  DevBuf dA, dT, dst;
+  const int64_t ld = round_up(N, 2);
+  CUDA_TRY(cudaMalloc(&dA.p, sizeof(double) * (size_t)N * ld));
+  CUDA_TRY(cudaMalloc(&dT.p, sizeof(double) * NB * NB));
+  CUDA_TRY(cudaMalloc(&dst.p, sizeof(double) * 8));
+  CUDA_TRY(cudaMemsetAsync(dst.p, 0, sizeof(double) * 8, st));
+  CUDA_TRY(cudaMemcpy2DAsync(dA.p, sizeof(double) * ld, A, sizeof(double) * N, sizeof(double) * N, N, cudaMemcpyHostToDevice, st));
+  GP_TRY(factorise(dA.as<double>(), N, ld, nullptr, nullptr, nullptr, dT.as<double>(), dst.as<double>(), st));
+  double state[8];
+  CUDA_TRY(cudaMemcpyAsync(state, dst.p, sizeof state, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (state[1] != 0.0) return fail(GPLVM_ERR_NUMERIC, "gplvm_cholesky: matrix not positive definite (panel %d)", (int)state[1] - 1);
+  return copy_lower_to_host(dA.as<double>(), N, ld, L_out, st);
+}
+
+int gplvm_tri_solve_lower(const double* L, int64_t N, const double* B, int64_t R, double* X_out) {
+  if (!L || !B || !X_out) return fail(GPLVM_ERR_ARG, "gplvm_tri_solve_lower: null argument");
+  if (N < 1 || R < 1) return fail(GPLVM_ERR_ARG, "gplvm_tri_solve_lower: sizes must be positive");
+  GP_TRY(ensure_context());
+  Context& c = ctx();
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  CUDA_TRY(cudaSetDevice(c.shards[0].device));
+  cudaStream_t st = c.shards[0].stream;
+  GP_TRY(set_gemm_attrs());
+  DevBuf dL, dB, dX, dT, dst;
+  CUDA_TRY(cudaMalloc(&dL.p, sizeof(double) * (size_t)N * N));
+  CUDA_TRY(cudaMalloc(&dB.p, sizeof(double) * (size_t)N * R));
+  CUDA_TRY(cudaMalloc(&dX.p, sizeof(double) * (size_t)N * R));
+  CUDA_TRY(cudaMalloc(&dT.p, sizeof(double) * NB * NB));
+  CUDA_TRY(cudaMalloc(&dst.p, sizeof(double) * 8));
+  CUDA_TRY(cudaMemsetAsync(dst.p, 0, sizeof(double) * 8, st));
+  CUDA_TRY(cudaMemcpyAsync(dL.p, L, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dB.p, B, sizeof(double) * (size_t)N * R, cudaMemcpyHostToDevice, st));
+  const int diag_smem = DIAG_SMEM;
+  for (int64_t k0 = 0; k0 < N; k0 += NB) {
+    const int nb = (int)std::min<int64_t>(NB, N - k0);
+    GP_LAUNCH(tri_inverse_kernel, 1, 256, diag_smem, st, dL.as<double>(), N, k0, nb, dT.as<double>(), dst.as<double>());
+    GP_LAUNCH(tri_diag_apply_kernel, (unsigned)ceil_div(R, 256), 256, 0, st, dT.as<double>(), nb, dB.as<double>(), dX.as<double>(), R, k0);
+    const int64_t below = N - k0 - nb;
+    if (below > 0) {
+      for (int64_t b0 = 0; b0 < below; b0 += 32768) {
+        dim3 grid((unsigned)ceil_div(R, 256), (unsigned)std::min<int64_t>(32768, below - b0));
+        GP_LAUNCH(tri_update_kernel, grid, 256, 0, st, dL.as<double>() + b0 * N, N, N - b0, k0, nb, dX.as<double>(),
+                  dB.as<double>() + b0 * R, R);
+      }
+    }
+  }
+  double state[8];
+  CUDA_TRY(cudaMemcpyAsync(state, dst.p, sizeof state, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(X_out, dX.p, sizeof(double) * (size_t)N * R, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (state[1] != 0.0) return fail(GPLVM_ERR_NUMERIC, "gplvm_tri_solve_lower: singular triangular factor");
+  return GPLVM_OK;
+}
+
+}  // extern "C"

@@ -127,9 +127,14 @@ __global__ void __launch_bounds__(EW * 32) masked_estep_kernel(const double* __r
   for (int64_t n = (int64_t)blockIdx.x * EW + w; n < n_obs; n += nw) {
     double yy;
     const int cnt = masked_build(X + n * ldx, p, Mi, b, lane, yy);
-    if (cnt == 0 && lane == 0) p.scal[S_ERR] = 2.0;  // all-NaN observation: unsupported (Util.hs:81)
+    if (cnt == 0) {
+      if (lane == 0) set_err(p.scal, 2.0);
+      for (int a = lane; a < M; a += 32) Ez[n * M + a] = 0.0;
+      for (int e = lane; e < NV; e += 32) Av[n * NV + e] = 0.0;
+      continue;
+    }  // all-NaN observation: unsupported (Util.hs:81)
     const bool ok = warp_cholesky(Mi, M, lane);
-    if (!ok && lane == 0) p.scal[S_ERR] = 1.0;
+    if (!ok && lane == 0) set_err(p.scal, 1.0);
     // ez = (L L^T)^-1 b
     warp_forward(Mi, b, M, lane);
     warp_backward(Mi, b, M, lane);
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(EW * 32) masked_update_kernel(Par p, const dou
     scratch[d] = cd - 2.0 * wr + quad;
     scratch[D + d] = mdw;
     p.mu[d] = mu_new;
-    if (!ok) p.scal[S_ERR] = 1.0;
+    if (!ok) set_err(p.scal, 1.0);
   }
 }
 
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(256) masked_finalize_kernel(Par p, const doubl
     p.scal[S_DVAR] = dvar;
     p.scal[S_MAXDW] = m;
     p.scal[S_STEPS] += 1.0;
-    if (!(news2 > 0.0)) p.scal[S_ERR] = 1.0;
+    if (!(news2 > 0.0)) set_err(p.scal, 1.0);
     if (p.scal[S_USETOL] != 0.0 && !(fmax(dvar, m) > p.scal[S_TOL])) p.scal[S_DONE] = 1.0;
   }
   __syncthreads();
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(EW * 32) masked_ll_kernel(const double* __rest
     double yy;
     const int cnt = masked_build(X + n * ldx, p, Mi, b, lane, yy);
     const bool ok = warp_cholesky(Mi, M, lane);
-    if (!ok && lane == 0) p.scal[S_ERR] = 1.0;
+    if (!ok && lane == 0) set_err(p.scal, 1.0);
     warp_forward(Mi, b, M, lane);  // t = L^-1 W_i^T yc
     double tt = 0.0, ld = 0.0;
     for (int a = lane; a < M; a += 32) {
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(256) masked_restore_prep_kernel(Par p, double*
     for (int a = 0; a < M; ++a) t = fma(p.W[(int64_t)d * M + a], p.c[a], t);
     fm[d] = t;
   }
-  if (threadIdx.x == 0 && !ok) p.scal[S_ERR] = 1.0;
+  if (threadIdx.x == 0 && !ok) set_err(p.scal, 1.0);
 }
 
 // out[d][i] = B_d . ez_i + fm_d for a chunk of observations; out is feature-major (D x ld)

@@ -38,6 +38,13 @@ struct Par {
   long long N;   // global number of observations
 };
 
+#ifdef __CUDACC__
+// numeric-failure flag: 1 = not positive definite, 2 = an observation with every feature missing (sticky)
+__device__ __forceinline__ void set_err(double* scal, double code) {
+  if (code == 2.0 || scal[S_ERR] == 0.0) scal[S_ERR] = code;
+}
+#endif
+
 struct ShardState {
   int dev = 0;
   cudaStream_t st = nullptr;

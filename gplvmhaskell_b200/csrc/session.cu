@@ -110,6 +110,8 @@ static int check_async(gplvm_ppca_session* s, double* scal_out) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     CUDA_TRY(cudaMemcpyAsync(scal, sh.par.scal, sizeof scal, cudaMemcpyDeviceToHost, sh.st));
     CUDA_TRY(cudaStreamSynchronize(sh.st));
+    if (scal[S_ERR] == 2.0)
+      return fail(GPLVM_ERR_UNSUPPORTED, "missing-data PPCA: an observation has every feature missing (unsupported by the reference, Util.hs:81)");
     if (scal[S_ERR] != 0.0)
       return fail(GPLVM_ERR_NUMERIC, "PPCA: a matrix that must be positive definite is not (step %lld)", (long long)scal[S_STEPS]);
     if (&sh == &s->sh[0] && scal_out) memcpy(scal_out, scal, sizeof scal);

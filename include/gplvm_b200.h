@@ -160,6 +160,9 @@ int gplvm_session_loglik(gplvm_ppca_session* s, double* loglik_out);
  * sessions only, after at least one step. */
 int gplvm_session_restored(gplvm_ppca_session* s, double* restored, int64_t ld);
 
+/* Switch the per-kernel CUDA-event bracket of the dominant statistics pass on or off (off by default). */
+int gplvm_session_set_kernel_timing(gplvm_ppca_session* s, int on);
+
 /* Device time in milliseconds of the last `gplvm_session_steps` batch on this process (max over the
  * local GPUs), measured with CUDA events on the launching streams; blocks until the batch is done.
  * kernel_ms (nullable) receives the summed duration of the dominant statistics kernel only. */

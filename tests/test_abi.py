@@ -1,0 +1,75 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports every symbol include/gplvm_b200.h
+declares, and refuses to compute without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gplvmhaskell_b200 as g
+from gplvmhaskell_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "gplvm_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gplvm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = g.load_library()
+    names = header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libgplvm_b200.so lacks %s" % n
+    # and the ctypes table covers the header exactly
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_error_strings():
+    lib = g.load_library()
+    assert b"sm_100a" in lib.gplvm_version()
+    assert lib.gplvm_last_error() is not None
+
+
+def test_argument_validation_happens_before_cuda():
+    lib = g.load_library()
+    rc = lib.gplvm_ppca_dense(None, 4, 10, 2, None, 1.0, 0, 1, 0.0, None, None, None, None)
+    assert rc == _lib.ERR_ARG
+    assert b"null" in lib.gplvm_last_error()
+    rc = lib.gplvm_set_devices(0)
+    assert rc == _lib.ERR_ARG
+
+
+def test_typesafe_checks_raise_reference_messages_before_ffi():
+    Y = np.zeros((4, 10))
+    with pytest.raises(ValueError, match="dimensions x2 and d1 should be equal, but they are not"):
+        g.make_ppca_type_safe(Y, 3, g.Left(1), (np.zeros((4, 2)), 1.0))
+    with pytest.raises(ValueError, match="dimensions y1 and y2 should be equal, but they are not"):
+        g.make_ppca_type_safe(Y, 3, g.Left(1), (np.zeros((5, 3)), 1.0))
+    with pytest.raises(ValueError, match="Input matrix should have at least one column"):
+        g.make_ppca_type_safe(np.zeros((4, 0)), 3, g.Left(1), (np.zeros((4, 3)), 1.0))
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device refusal cannot be observed")
+    with pytest.raises(g.GplvmError) as ei:
+        g.make_ppca(np.random.default_rng(0).standard_normal((4, 10)), 2, g.Left(1), 0)
+    assert ei.value.code == _lib.ERR_CUDA
+    assert "no CPU fallback" in ei.value.message
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle: no file of the package mentions it."""
+    pkg = os.path.join(ROOT, "gplvmhaskell_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep)[-1:]:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f

@@ -1,0 +1,127 @@
+"""CPU tests of the oracle (test infrastructure): golden fixtures, closed-form known answers and the
+agreement between its literal and sufficient-statistics formulations.  No GPU needed."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import gp as ogp
+from oracle import ppca as oppca
+from conftest import rel
+
+
+def test_golden_dense_regenerates(iris):
+    r = oppca.em_steps_fast(iris["Y"], iris["W0"], 1.0, ("left", 0))
+    assert rel(r.W, iris["dense_s1_k0_W"]) < 1e-13
+    assert abs(r.variance - float(iris["dense_s1_k0_var"])) < 1e-13 * abs(r.variance)
+    assert abs(r.final_exp_likelihood - float(iris["dense_s1_k0_ll"])) < 1e-12 * abs(r.final_exp_likelihood)
+    assert r.steps_done == 1
+
+
+def test_golden_missing_regenerates(iris):
+    r = oppca.em_steps_missed(iris["Yn"], iris["W0"], 1.0, ("left", 1))
+    assert r.steps_done == 2
+    assert rel(r.W, iris["miss_s1_k1_W"]) < 1e-12
+    assert rel(r.restored_matrix, iris["miss_s1_k1_restored"]) < 1e-12
+    assert abs(r.variance - float(iris["miss_s1_k1_var"])) < 1e-12 * r.variance
+
+
+def test_dense_fixed_point_is_tipping_bishop(iris):
+    """Known answer independent of the oracle: at the EM fixed point sigma2 is the mean of the discarded
+    eigenvalues of the (1/N) covariance and span(W) the leading eigenvectors (Tipping & Bishop 1999)."""
+    Y = iris["Y"]
+    d, n = Y.shape
+    Xc = Y - Y.mean(axis=1, keepdims=True)
+    S = Xc @ Xc.T / n
+    ev, U = np.linalg.eigh(S)
+    r = oppca.em_steps_fast(Y, iris["W0"], 1.0, ("left", 4000))
+    assert abs(r.variance - ev[0]) < 1e-8 * ev[0]
+    P = oppca.projector(r.W)
+    Pref = U[:, 1:] @ U[:, 1:].T
+    assert np.max(np.abs(P - Pref)) < 1e-6
+    # SURVEY.md 8c cross-check value
+    assert abs(ev[0] - 0.023676192353627) < 1e-12
+
+
+def test_golden_1001_steps_known_values(iris):
+    assert abs(float(iris["dense_sbig_k1000_ll"]) - (-381.92805336)) < 1e-6
+    assert abs(float(iris["miss_s1_k1000_var"]) - 0.0199236485) < 1e-7  # SURVEY 8c probe value (other init)
+    assert abs(float(iris["miss_s1_k1000_ll"]) - (-344.89248114)) < 1e-5
+
+
+def test_left_runs_k_plus_one_steps(iris):
+    for k in (0, 1, 5):
+        assert oppca.em_steps_fast(iris["Y"], iris["W0"], 1.0, ("left", k)).steps_done == k + 1
+    assert oppca.em_steps_fast(iris["Y"], iris["W0"], 1.0, ("left", -3)).steps_done == 1
+
+
+def test_right_tolerance_rule(iris):
+    r = oppca.em_steps_fast(iris["Y"], iris["W0"], 1.0, ("right", 1e-6))
+    assert r.steps_done == int(iris["dense_s1_tol_steps"])
+    assert rel(r.W, iris["dense_s1_tol_W"]) < 1e-12
+
+
+def test_masked_vectorised_equals_literal(iris):
+    Yn, W0 = iris["Yn"], iris["W0"]
+    mu = np.zeros(4)
+    W, s2 = W0.copy(), 1.0
+    for _ in range(3):
+        a = oppca.missed_step_literal(Yn, mu, W, s2)
+        b = oppca.missed_step_vectorised(Yn, mu, W, s2)
+        assert rel(b[0], a[0]) < 1e-12 and rel(b[1], a[1]) < 1e-12
+        assert abs(b[2] - a[2]) < 1e-12 * a[2]
+        assert rel(b[5]["EX"], a[5]["EX"]) < 1e-12
+        mu, W, s2 = a[0], a[1], a[2]
+    ll_a = oppca.missed_loglik_literal(Yn, mu, W, s2, a[5]["known"])
+    ll_b = oppca.missed_loglik_vectorised(Yn, mu, W, s2)
+    assert abs(ll_a - ll_b) < 1e-12 * abs(ll_a)
+
+
+def test_masked_on_dense_data_without_nan_is_consistent():
+    """Property: with no NaN the masked step's E-step equals the dense E-step with mu_0 = 0 (un-centred)."""
+    rng = np.random.default_rng(0)
+    Y = rng.standard_normal((6, 40))
+    W0 = rng.standard_normal((6, 2))
+    mu, W, s2, *_ = oppca.missed_step_literal(Y, np.zeros(6), W0, 0.7)
+    Minv = np.linalg.inv(W0.T @ W0 + 0.7 * np.eye(2))
+    EX = Minv @ W0.T @ Y
+    assert rel(mu, (Y - W0 @ EX).mean(axis=1)) < 1e-12
+
+
+def test_dispatch_on_nan_sum(iris):
+    assert oppca.make_ppca(iris["Y"], iris["W0"], 1.0, ("left", 0)).no_missed_data
+    r = oppca.make_ppca(iris["Yn"], iris["W0"], 1.0, ("left", 0))
+    assert not r.no_missed_data and r.restored_matrix.shape == (4, 150)
+
+
+def test_typesafe_dimension_checks():
+    oppca.check_typesafe_dims((4, 150), (4, 3), 3)
+    with pytest.raises(ValueError, match="x2 and d1"):
+        oppca.check_typesafe_dims((4, 150), (4, 2), 3)
+    with pytest.raises(ValueError, match="y1 and y2"):
+        oppca.check_typesafe_dims((4, 150), (5, 3), 3)
+    with pytest.raises(ValueError, match="at least one column"):
+        oppca.check_typesafe_dims((4, 0), (4, 3), 3)
+
+
+def test_gp_oracle_golden(gp_golden):
+    g = gp_golden
+    K = ogp.kernel_function(g["x_train"], g["x_train"])
+    assert np.array_equal(K, g["K"])
+    Ks = ogp.kernel_function(g["x_test"], g["x_train"])
+    assert Ks.shape == (5, 50) and np.array_equal(Ks, g["Ks"])     # len(v2) x len(v1), GPExample.hs:83
+    # closed form: k(a, b) = exp(-5 (a - b)^2)
+    a, b = g["x_test"][7], g["x_train"][2]
+    assert abs(Ks[2, 7] - math.exp(-5.0 * (a - b) ** 2)) < 1e-12
+    L, lml = ogp.gp_chol_lml(g["x_train"][:, None], g["y_train"], np.array([10.0]), 1.0, 0.00005)
+    assert np.allclose(L @ L.T, K + 5e-5 * np.eye(5), atol=1e-14)
+    # LML against the textbook formula with an explicit inverse
+    Kj = K + 5e-5 * np.eye(5)
+    ref = -0.5 * g["y_train"] @ np.linalg.solve(Kj, g["y_train"]) - 0.5 * np.linalg.slogdet(Kj)[1] - 2.5 * math.log(2 * math.pi)
+    assert abs(lml - ref) < 1e-10 * abs(ref)
+
+
+def test_ard_reduces_to_reference_kernel(gp_golden):
+    g = gp_golden
+    K1 = ogp.ard_kernel(g["x_test"][:, None], g["x_train"][:, None], np.array([1.0 / 0.1]), 1.0)
+    assert np.array_equal(K1, g["Ks"])
