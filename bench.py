@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- PPCA EM iterations/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|missing|gp] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A "step" is one EM iteration over the whole observation matrix (E-step statistics, all-reduce, M-step).
+Workload at every N: synthetic dense PPCA, N_obs = 2^23, D = 256, M = 16, FP64 (BASELINE.json config
+"N=8M, D=256, M=16"), generated on the device by the library's counter-based generator;
+with N > 1 GPUs the SAME 2^23 observations are row-sharded over the ranks (strong scaling) and one packed
+NCCL all-reduce per step combines the partial statistics.
+
+value   : EM iterations/s with the observations resident in HBM; device time of exactly K steps (CUDA events
+          on the library's stream), max over ranks, after W warm-up steps.  Inputs (17.2 GB at N=1) are far
+          larger than the 126 MB L2, so no flush is needed between steps.
+e2e     : the same metric through the reference-facing C-ABI call with HOST buffers: gplvm_ppca_dense
+          (one H2D of Y in reference layout, K EM steps, the log-likelihood pass, D2H of W/sigma2/LL), wall
+          clock around the call.  N > 1: the session API per rank on that rank's host shard.
+roofline: the dominant kernel (dense statistics pass) against the FP64 tensor (DMMA) peak measured in-run by
+          the library's register-resident DMMA probe (MEASURED_PEAKS.json has no FP64 entry) and against
+          MEASURED_PEAKS.json's HBM copy bandwidth.
+cpu_baseline / --impl reference: the reference cannot be built (no GHC); the CPU arm is the NumPy/OpenBLAS
+          oracle that restates src/GPLVM/PPCA.hs:54-94 in the reference's literal operation order ("port"),
+          on all host cores, each step on a bounded sample of 2^18 observations, scaled linearly to 2^23.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, M = 256, 16
+N_FULL = 1 << 23
+SEED = 1234
+CPU_SAMPLE = 1 << 18
+
+
+def flops_per_obs_dense(d=D, m=M):
+    return 4 * d * m + 2 * m * m   # X.A, X^T.Ez (2DM each) + Ez^T Ez (M^2 multiply-adds)
+
+
+def bytes_per_obs(d=D):
+    return 8 * d
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_rate(steps: int, warmup: int, sample: int = CPU_SAMPLE):
+    """Oracle dense EM step (literal reference op order) on a bounded sample; returns (it/s at N_FULL, info)."""
+    import numpy as np
+    from oracle import ppca as oppca
+    rng = np.random.default_rng(SEED)
+    Wt = rng.standard_normal((D, M))
+    Y = Wt @ rng.standard_normal((M, sample)) + rng.standard_normal((D, 1)) + rng.standard_normal((D, sample))
+    Xc = oppca.center_dense(Y)
+    W = np.random.default_rng(4321).standard_normal((D, M))
+    s2 = 1.0
+    for _ in range(warmup):
+        W, s2, _, _ = oppca.dense_step(Xc, W, s2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        W, s2, _, _ = oppca.dense_step(Xc, W, s2)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    rate_sample = 1.0 / dt
+    rate_full = rate_sample * sample / N_FULL
+    return rate_full, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    rate, dt = cpu_port_rate(args.steps, max(1, min(args.warmup, 2)))
+    sample = ("dense_step of oracle/ppca.py (NumPy/OpenBLAS restatement of PPCA.hs:63-82, literal op order) on 2^18 "
+              "of the 2^23 observations per step, scaled linearly to 2^23; the GHC reference cannot be built (no GHC)")
+    line = {"impl": "reference", "metric": "PPCA EM iterations/sec (N=8M,D=256,M=16,FP64)", "value": rate,
+            "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": "dense PPCA EM N=2^23 D=256 M=16 FP64 (CPU oracle, sampled)"},
+            "cpu_baseline": {"value": rate, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dense", choices=["dense", "missing", "gp"])
+    ap.add_argument("--nobs", type=int, default=None, help="override the number of observations (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import ctypes as C
+    import gplvmhaskell_b200 as g
+    from gplvmhaskell_b200 import _lib
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; libgplvm_b200 has no CPU fallback"}))
+        return 2
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        print(json.dumps({"error": "launch with torch.distributed.run for --gpus > 1"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    lib = g.load_library()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            _lib.check(lib.gplvm_dist_unique_id(raw))
+            idbuf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        _lib.check(lib.gplvm_dist_init(rank, world, local_rank, raw))
+    else:
+        _lib.check(lib.gplvm_dist_init(0, 1, local_rank, None))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    missing = args.workload == "missing"
+    n_obs = args.nobs or N_FULL
+    per = (n_obs + world - 1) // world
+    begin = per * rank
+    count = min(per, n_obs - begin)
+    W0 = np.random.default_rng(4321).standard_normal((D, M))
+
+    sess = g.Session(D, n_obs, M, missing=missing, obs_begin=begin, obs_count=count)
+    sess.synth(SEED, 0.2 if missing else 0.0)
+    sess.init(W0, 1.0)
+    sess.steps(args.warmup)
+    sess.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.gplvm_kernel_launches()
+    barrier()
+    sess.steps(args.steps)
+    sess.sync()
+    barrier()
+    launches = lib.gplvm_kernel_launches() - launches0
+    total_ms, _ = sess.last_steps_ms()
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # dominant kernel: statistics pass, timed per launch with CUDA events on the launching stream
+    sess.set_kernel_timing(True)
+    kms = []
+    for _ in range(min(args.steps, 10)):
+        sess.steps(1)
+        kms.append(sess.last_steps_ms()[1])
+    sess.set_kernel_timing(False)
+    k_ms = max_over_ranks(sum(kms) / len(kms))
+    p = sess.params()
+    ll = sess.loglik()
+
+    peaks, peak_kind = measured_peaks()
+    dmma = C.c_double()
+    _lib.check(lib.gplvm_probe_dmma_tflops(C.byref(dmma)))
+    if missing:
+        # ~52 394 flop / observation (complement form, 20 % NaN); FP64-compute bound
+        flop_obs = 52394.0
+    else:
+        flop_obs = float(flops_per_obs_dense())
+    ach_tf = flop_obs * count / (k_ms * 1e-3) * 1e-12
+    ach_gbs = bytes_per_obs() * count / (k_ms * 1e-3) * 1e-9
+    roofline = {"bound": "tensor", "achieved": ach_tf, "peak": dmma.value, "unit": "TFLOP/s", "frac": ach_tf / dmma.value,
+                "traffic": None, "kernel": "dense statistics pass (X.A, X^T.Ez, Ez^T.Ez) per rank",
+                "kernel_ms": k_ms, "peak_source": "in-run DMMA.8x8x4 register-chain probe (no FP64 entry in MEASURED_PEAKS.json); "
+                "cublasDgemm 8192^3 measured 35.8 TFLOP/s (profiles/r1_fp64_peaks.log)",
+                "hbm_achieved_gbs": ach_gbs, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_frac": ach_gbs / peaks.get("hbm_gbs"),
+                "hbm_peak_source": peak_kind, "flop_per_obs": flop_obs, "bytes_per_obs": bytes_per_obs()}
+
+    # ---- e2e: host buffers through the C ABI -----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((D, count), dtype=torch.float64, pin_memory=True)
+        Yh = host.numpy()
+        _lib.check(lib.gplvm_session_read_data(sess.h, _lib.dptr(Yh), count))   # same synthetic data, now on the host
+        sess.close()
+        Wout = np.empty((D, M)); s2o, llo, st = C.c_double(), C.c_double(), C.c_int64()
+        if world == 1 and not missing:
+            small = np.ascontiguousarray(Yh[:, :4096])
+            _lib.check(lib.gplvm_ppca_dense(_lib.dptr(small), D, 4096, M, _lib.dptr(W0), 1.0, 0, 1, 0.0, _lib.dptr(Wout),
+                                            C.byref(s2o), C.byref(llo), C.byref(st)))
+            barrier()
+            t0 = time.perf_counter()
+            _lib.check(lib.gplvm_ppca_dense(_lib.dptr(Yh), D, count, M, _lib.dptr(W0), 1.0, 0, args.steps - 1, 0.0,
+                                            _lib.dptr(Wout), C.byref(s2o), C.byref(llo), C.byref(st)))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            assert st.value == args.steps
+            d2h = 8 * (D * M + 2)
+        else:
+            barrier()
+            t0 = time.perf_counter()
+            s2 = g.Session(D, n_obs, M, missing=missing, obs_begin=begin, obs_count=count)
+            s2.load_host(Yh)
+            s2.init(W0, 1.0)
+            s2.steps(args.steps)
+            pp = s2.params()
+            llv = s2.loglik()
+            d2h = 8 * (D * M + 2)
+            if missing:
+                R = torch.empty((D, count), dtype=torch.float64, pin_memory=True)
+                _lib.check(lib.gplvm_session_restored(s2.h, _lib.dptr(R.numpy()), count))
+                d2h += 8 * D * count
+            barrier()
+            dt = time.perf_counter() - t0
+            s2.close()
+        dt = max_over_ranks(dt)
+        e2e = {"value": args.steps / dt, "unit": "iterations/s", "h2d_bytes_per_step": 8 * D * count * world / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": dt,
+               "what": "one C-ABI call on host buffers: H2D of Y (reference D x N layout, pinned) once + %d EM steps + "
+                       "log-likelihood pass + D2H of W, sigma2, LL%s" % (args.steps, " + restored matrix" if missing else "")}
+    else:
+        sess.close()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, dt_step = cpu_port_rate(steps=12, warmup=1)
+        cpu_baseline = {"value": rate, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": "oracle/ppca.py dense_step (NumPy/OpenBLAS restatement of PPCA.hs:63-82, literal op order), "
+                                  "12 steps on 2^18 of the 2^23 observations (%.2f s/step), scaled linearly to 2^23" % dt_step}
+
+    if rank == 0:
+        line = {"metric": "PPCA EM iterations/sec (N=8M,D=256,M=16,FP64)", "value": value, "unit": "iterations/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s PPCA EM N=%d D=%d M=%d FP64%s" % (args.workload, n_obs, D, M,
+                                                                              " 20% NaN" if missing else ""),
+                           "sharding": "observations row-sharded over %d rank(s), one packed NCCL all-reduce per step" % world,
+                           "l2": "inputs (%.1f GB per rank) exceed the 126 MB L2; no flush" % (8 * D * count / 1e9),
+                           "init": "W0 ~ N(0,1) seed 4321, sigma2_0 = 1"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "sigma2": p["sigma2"], "loglik": ll}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        lib.gplvm_dist_finalize()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
