@@ -3,12 +3,13 @@
 // log-likelihood.  The fused FP64 tensor-core statistics kernel for the benchmark shape lives in
 // dense_dmma.cu; everything else (reduction of partials, update, LL) is shared.
 //
-// Single-pass formulation (X = observation-major view of Y, Xc = X - mean):
-//   prep   : Minv = (s2 I + W^T W)^-1,  A = W Minv,  c = mean^T A                   (PPCA.hs:65-66)
-//   stats  : ez_n = x_n^T A - c  (= Minv W^T xc_n, PPCA.hs:67);
-//            XEz = sum_n x_n ez_n^T, EE = sum_n ez_n ez_n^T, sEz = sum_n ez_n        (PPCA.hs:68-69)
-//   update : XEzc = XEz - mean sEz^T; Ezz = N s2 Minv + EE; W' = XEzc Ezz^-1          (PPCA.hs:69,74)
-//            s2' = (|Xc|^2 - 2 tr(W'^T XEzc) + |W' U^T|^2) / (N D), U = chol(Ezz)     (PPCA.hs:75-80)
+// Single-pass formulation.  The resident observations are centred ONCE, in place
+// (Xc = X - feature mean, PPCA.hs:61; the reference re-evaluates the delayed subtraction in every product):
+//   prep   : Minv = (s2 I + W^T W)^-1,  A = W Minv                                   (PPCA.hs:65-66)
+//   stats  : ez_n = xc_n^T A  (= Minv W^T xc_n, PPCA.hs:67);
+//            XEz = sum_n xc_n ez_n^T, EE = sum_n ez_n ez_n^T                         (PPCA.hs:68-69)
+//   update : Ezz = N s2 Minv + EE; W' = XEz Ezz^-1                                   (PPCA.hs:69,74)
+//            s2' = (|Xc|^2 - 2 tr(W'^T XEz) + |W' U^T|^2) / (N D), U = chol(Ezz)     (PPCA.hs:75-80)
 //   loglik : PPCA.hs:83-89 through the determinant lemma / Woodbury (no D x D matrix).
 #include "ppca.cuh"
 
@@ -25,10 +26,9 @@ template <int KIND>
 __device__ __forceinline__ double row_value(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Ez,
                                             int ldez, int D, int MPd, int64_t n, int r) {
   if (KIND == ROWS_DENSE) {
-    // rows: [0,D) features of X | [D, D+MP) components of ez | D+MP: ones
+    // rows: [0,D) features of Xc | [D, D+MP) components of ez
     if (r < D) return X[n * ldx + r];
-    if (r < D + MPd) return Ez[n * ldez + (r - D)];
-    return 1.0;
+    return Ez[n * ldez + (r - D)];
   } else {
     // rows: [0,D) observed flag | [D,2D) observed value | 2D: ones
     if (r < D) return isnan(X[n * ldx + r]) ? 0.0 : 1.0;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
   stats[i] = a;
 }
 
-// per-feature moments of the local observations.  mode 0: sum x; 1: sum (x-mean)^2;
+// per-feature moments of the local observations.  mode 0: sum x; 1: sum (x-mean)^2; 3: sum x^2;
 // 2 (masked): [count | sum | sum of squares] over the known entries.
 __global__ void __launch_bounds__(256) moments_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, int D, int mode,
                                                       const double* __restrict__ mean, double* __restrict__ partials,
@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const double* __restrict__
       const double v = X[n * ldx + d];
       if (mode == 0) a0 += v;
       else if (mode == 1) { const double t = v - m; a0 = fma(t, t, a0); }
+      else if (mode == 3) a0 = fma(v, v, a0);
       else if (!isnan(v)) { a0 += 1.0; a1 += v; a2 = fma(v, v, a2); }
     }
   }
@@ -151,10 +152,20 @@ __global__ void __launch_bounds__(256) moments_kernel(const double* __restrict__
   }
 }
 
-// ez_n = x_n^T A - c for the generic path (materialised like the reference's expEznZ, PPCA.hs:67)
+// Xc = X - mean, in place (PPCA.hs:61 -> Util.hs:175-178); sign = +1 undoes it (gplvm_session_read_data)
+__global__ void __launch_bounds__(256) centre_kernel(double* __restrict__ X, int64_t ldx, int64_t n_obs, int D,
+                                                     const double* __restrict__ mean, double sign) {
+  const int64_t total = n_obs * D;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = e / D;
+    const int d = (int)(e - n * D);
+    X[n * ldx + d] = fma(sign, mean[d], X[n * ldx + d]);
+  }
+}
+
+// ez_n = xc_n^T A for the generic path (materialised like the reference's expEznZ, PPCA.hs:67)
 __global__ void __launch_bounds__(256) dense_ez_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, Par p,
-                                                       const double* __restrict__ A, const double* __restrict__ c,
-                                                       double* __restrict__ Ez) {
+                                                       const double* __restrict__ A, double* __restrict__ Ez) {
   if (p.scal[S_DONE] != 0.0) return;
   extern __shared__ double sm[];
   const int MP = p.MP, D = p.D;
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(256) dense_ez_kernel(const double* __restrict_
   if (n < n_obs) {
 #pragma unroll
     for (int j = 0; j < GPLVM_MAX_M / 8 + 1; ++j)
-      if (j < nj && ty + 8 * j < MP) Ez[n * MP + ty + 8 * j] = acc[j] - c[ty + 8 * j];
+      if (j < nj && ty + 8 * j < MP) Ez[n * MP + ty + 8 * j] = acc[j];
   }
 }
 
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(256) dense_ez_kernel(const double* __restrict_
 // replicated parameter kernels (single CTA; identical on every GPU after the all-reduce)
 // ------------------------------------------------------------------------------------------------
 
-// Minv = (s2 I + W^T W)^-1 (Cholesky), logdet over the first M pivots, A = W Minv, c = mean^T A.
+// Minv = (s2 I + W^T W)^-1 (Cholesky), logdet over the first M pivots, A = W Minv.
 // sm: 2 * MP * MP doubles.
 __device__ void dense_prep_block(const Par& p, double* sm) {
   const int D = p.D, MP = p.MP, M = p.M;
@@ -225,13 +236,6 @@ __device__ void dense_prep_block(const Par& p, double* sm) {
     p.A[e] = t;
   }
   __syncthreads();
-  __threadfence_block();
-  for (int b = threadIdx.x; b < MP; b += blockDim.x) {
-    double t = 0.0;
-    for (int d = 0; d < D; ++d) t = fma(p.mu[d], p.A[(int64_t)d * MP + b], t);
-    p.c[b] = t;
-  }
-  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) dense_prep_kernel(Par p) {
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(256) dense_prep_kernel(Par p) {
   dense_prep_block(p, sm);
 }
 
-// stats layout: XEz [D x MP] | EE [MP x MP] | sEz [MP]
+// stats layout: XEz [D x MP] | EE [MP x MP]
 // sm: 2*MP*MP + 64 doubles
 __global__ void __launch_bounds__(256) dense_update_kernel(Par p, const double* __restrict__ stats) {
   extern __shared__ double sm[];
@@ -249,7 +253,6 @@ __global__ void __launch_bounds__(256) dense_update_kernel(Par p, const double* 
   double* red = sm + 2 * MP * MP;   // 33
   const double* XEz = stats;
   const double* EE = stats + (int64_t)D * MP;
-  const double* sEz = EE + MP * MP;
   const double s2 = p.scal[S_SIGMA2];
   const double Nd = (double)p.N;
   for (int e = threadIdx.x; e < MP * MP; e += blockDim.x) Ezz[e] = Nd * s2 * p.Minv[e] + EE[e];
@@ -259,8 +262,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(Par p, const double* 
   double second = 0.0, third = 0.0, maxdw = 0.0;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     double x[GPLVM_MAX_M], b[GPLVM_MAX_M];
-    const double md = p.mu[d];
-    for (int a = 0; a < MP; ++a) { b[a] = XEz[(int64_t)d * MP + a] - md * sEz[a]; x[a] = b[a]; }
+    for (int a = 0; a < MP; ++a) { b[a] = XEz[(int64_t)d * MP + a]; x[a] = b[a]; }
     chol_solve_vec(Ezz, MP, MP, x);
     for (int a = 0; a < MP; ++a) {
       second = fma(x[a], b[a], second);
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(Par p, const double* 
 
 // LL = -(N/2) (D log 2pi + log det C + tr(C^-1 S)),  S = Xc Xc^T / (N-1)            (PPCA.hs:87-89)
 //   log det C = (D-M) log s2 + log det(s2 I + W^T W);  tr(C^-1 S) = (tr S - tr(Minv W^T S W)) / s2
-// stats (from a statistics pass with A := W, c := mean^T W): EE = sum_n t_n t_n^T, t_n = W^T xc_n.
+// stats (from a statistics pass with A := W): EE = sum_n t_n t_n^T, t_n = W^T xc_n.
 __global__ void dense_ll_kernel(Par p, const double* __restrict__ stats) {
   if (threadIdx.x != 0) return;
   const int D = p.D, MP = p.MP, M = p.M;
@@ -322,15 +324,6 @@ __global__ void dense_set_total_kernel(Par p, const double* __restrict__ sums) {
     p.scal[S_TOTAL] = t;
   }
 }
-// c_ll = mean^T W  (into p.c; restored by the next prep)
-__global__ void dense_ll_c_kernel(Par p) {
-  for (int b = threadIdx.x; b < p.MP; b += blockDim.x) {
-    double t = 0.0;
-    for (int d = 0; d < p.D; ++d) t = fma(p.mu[d], p.W[(int64_t)d * p.MP + b], t);
-    p.c[b] = t;
-  }
-}
-
 int splits_for(int64_t n_obs, int64_t unit, int tiles_xy) {
   // aim for ~4 CTAs per SM over the whole grid
   int64_t want = ceil_div(148 * 4, tiles_xy > 0 ? tiles_xy : 1);
@@ -385,32 +378,47 @@ static int launch_moments(gplvm_ppca_session* s, int mode) {
 
 int moments_pass(gplvm_ppca_session* s, int mode) { return launch_moments(s, mode); }
 
-int dense_init_constants(gplvm_ppca_session* s) {
-  // feature means (Util.hs:159-164 on the transposed matrix), then |Xc|_F^2 (PPCA.hs:77)
-  GP_TRY(launch_moments(s, 0));
-  GP_TRY(session_allreduce_stats(s, s->D));
+int dense_centre(gplvm_ppca_session* s, double sign) {
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
-    GP_LAUNCH(dense_set_mean_kernel, 4, 256, 0, sh.st, sh.par, sh.stats);
+    GP_LAUNCH(centre_kernel, 148 * 8, 256, 0, sh.st, sh.X, sh.ldx, sh.n, (int)s->D, sh.par.mu, sign);
   }
-  GP_TRY(launch_moments(s, 1));
-  GP_TRY(session_allreduce_stats(s, s->D));
+  return GPLVM_OK;
+}
+
+int dense_init_constants(gplvm_ppca_session* s) {
+  // feature means (Util.hs:159-164 on the transposed matrix), centring in place (PPCA.hs:61), then |Xc|_F^2 (PPCA.hs:77)
+  if (!s->centred) {
+    GP_TRY(launch_moments(s, 0));
+    GP_TRY(session_allreduce_stats(s, s->D));
+    for (ShardState& sh : s->sh) {
+      CUDA_TRY(cudaSetDevice(sh.dev));
+      GP_LAUNCH(dense_set_mean_kernel, 4, 256, 0, sh.st, sh.par, sh.stats);
+    }
+    GP_TRY(dense_centre(s, -1.0));
+    s->centred = true;
+    GP_TRY(launch_moments(s, 3));
+    GP_TRY(session_allreduce_stats(s, s->D));
+    for (ShardState& sh : s->sh) {
+      CUDA_TRY(cudaSetDevice(sh.dev));
+      GP_LAUNCH(dense_set_total_kernel, 1, 32, 0, sh.st, sh.par, sh.stats);
+    }
+  }
   const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
-    GP_LAUNCH(dense_set_total_kernel, 1, 32, 0, sh.st, sh.par, sh.stats);
     GP_LAUNCH(dense_prep_kernel, 1, 256, smem, sh.st, sh.par);
   }
   return GPLVM_OK;
 }
 
-// statistics pass with projection matrix A (D x MP) and offset c (MP): fills sh.stats (local sums)
-static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double* A, const double* c) {
-  if (s->use_dmma) return dense_dmma_stats(s, sh, A, c);
+// statistics pass with projection matrix proj (D x MP): fills sh.stats (local sums)
+static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double* proj) {
+  if (s->use_dmma) return dense_dmma_stats(s, sh, proj);
   const int MP = s->MP, D = (int)s->D;
   const size_t smem = sizeof(double) * (64 * MP + 32 * 65);
-  GP_LAUNCH(dense_ez_kernel, (unsigned)ceil_div(sh.n, 32), 256, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, A, c, sh.Ez);
-  const int R = D + MP + 1;
+  GP_LAUNCH(dense_ez_kernel, (unsigned)ceil_div(sh.n, 32), 256, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, proj, sh.Ez);
+  const int R = D + MP;
   return launch_stats_gemm(sh, ROWS_DENSE, D, R, R, MP, MP, sh.Ez, MP, MP, nullptr, 0, s->S);
 }
 
@@ -418,7 +426,7 @@ int dense_enqueue_step(gplvm_ppca_session* s) {
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (sh.evk0) CUDA_TRY(cudaEventRecord(sh.evk0, sh.st));
-    GP_TRY(dense_stats_pass(s, sh, sh.par.A, sh.par.c));
+    GP_TRY(dense_stats_pass(s, sh, sh.par.A));
     if (sh.evk1) CUDA_TRY(cudaEventRecord(sh.evk1, sh.st));
   }
   GP_TRY(session_allreduce_stats(s, s->S));
@@ -431,19 +439,15 @@ int dense_enqueue_step(gplvm_ppca_session* s) {
 }
 
 int dense_loglik(gplvm_ppca_session* s, double* ll) {
-  // one extra pass with the projection W (A := W, c := mean^T W): EE becomes W^T Xc Xc^T W
+  // one extra pass with the projection W (A := W): EE becomes W^T Xc Xc^T W
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
-    GP_LAUNCH(dense_ll_c_kernel, 1, 64, 0, sh.st, sh.par);
-    // the pass must run even after the tolerance rule has fired: clear DONE around it
-    GP_TRY(dense_stats_pass(s, sh, sh.par.W, sh.par.c));
+    GP_TRY(dense_stats_pass(s, sh, sh.par.W));
   }
   GP_TRY(session_allreduce_stats(s, s->S));
-  const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     GP_LAUNCH(dense_ll_kernel, 1, 32, 0, sh.st, sh.par, sh.stats);
-    GP_LAUNCH(dense_prep_kernel, 1, 256, smem, sh.st, sh.par);  // restore c (and A, Minv) for further steps
   }
   ShardState& s0 = s->sh[0];
   CUDA_TRY(cudaSetDevice(s0.dev));

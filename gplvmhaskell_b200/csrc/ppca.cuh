@@ -28,7 +28,7 @@ struct Par {
   double* mu;    // D        dense: feature means (constant); masked: EM mean
   double* A;     // D x MP   dense: W * Minv
   double* Minv;  // MP x MP  dense: (sigma2 I + W^T W)^-1 ; masked: C0 = sigma2 I + W^T W
-  double* c;     // MP       dense: mu^T A
+  double* c;     // MP       masked: mean of E[z_i] over the observations (restore)
   double* nd;    // D        masked: number of observations knowing feature d (global)
   double* sy;    // D        masked: sum of known y_d
   double* syy;   // D        masked: sum of known y_d^2
@@ -70,6 +70,7 @@ struct gplvm_ppca_session {
   int MP = 0, NV = 0;
   bool missing = false;
   bool has_data = false, initialised = false;
+  bool centred = false;    // dense: the resident observations have had their feature means subtracted (PPCA.hs:61)
   bool use_dmma = false;   // dense: fused DMMA kernel eligible
   int64_t S = 0;           // packed statistics length
   int64_t steps = 0;       // steps enqueued so far
@@ -85,7 +86,7 @@ int dense_loglik(gplvm_ppca_session* s, double* ll);
 // dense_dmma.cu
 bool dense_dmma_eligible(const gplvm_ppca_session* s);
 int dense_dmma_prepare(gplvm_ppca_session* s);
-int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* A, const double* c);
+int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int dense_dmma_release(gplvm_ppca_session* s);
 int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
 // masked.cu

@@ -6,6 +6,7 @@
 
 namespace gplvm {
 int moments_pass(gplvm_ppca_session* s, int mode);
+int dense_centre(gplvm_ppca_session* s, double sign);
 
 namespace {
 
@@ -142,13 +143,14 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
     return fail(GPLVM_ERR_ARG, "session_create: partial observation blocks need gplvm_dist_init (multi-process mode)");
   auto* s = new gplvm_ppca_session();
   s->D = D; s->N = N_global; s->M = M; s->missing = missing != 0;
-  s->MP = s->missing ? (int)M : (int)round_up(M, 8);
+  s->use_dmma = dense_dmma_eligible(s);
+  s->MP = s->missing ? (int)M : (s->use_dmma ? 16 : (int)round_up(M, 8));
   if (s->MP > GPLVM_MAX_M) s->MP = GPLVM_MAX_M;
   s->NV = s->MP * (s->MP + 1) / 2;
   if (s->missing)  // S1 | G  (D x (M+NV)) ; S2 (D x M) ; sum ez (M)
     s->S = D * (s->MP + s->NV) + (D + 1) * s->MP;
-  else             // XEz (D x MP) | EE (MP x MP) | sEz (MP)
-    s->S = (D + s->MP + 1) * s->MP;
+  else             // XEz (D x MP) | EE (MP x MP)
+    s->S = (D + s->MP) * s->MP;
   const int nsh = (int)c.shards.size();
   int used = nsh;
   if (obs_count < used) used = (int)obs_count;
@@ -165,7 +167,6 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
     delete s;
     return fail(GPLVM_ERR_ARG, "session_create: fewer observations than GPUs");
   }
-  s->use_dmma = dense_dmma_eligible(s);
   const int MP = s->MP;
   for (ShardState& sh : s->sh) {
     cudaError_t e = cudaSetDevice(sh.dev);
@@ -252,6 +253,7 @@ int gplvm_session_load_host(gplvm_ppca_session* s, const double* Y, int64_t ld) 
   }
   s->has_data = true;
   s->initialised = false;
+  s->centred = false;
   return GPLVM_OK;
 }
 
@@ -262,6 +264,8 @@ int gplvm_session_read_data(gplvm_ppca_session* s, double* Y, int64_t ld) {
   if (!s->has_data) return fail(GPLVM_ERR_STATE, "session_read_data: no data loaded");
   std::lock_guard<std::recursive_mutex> lk(ctx().mu);
   const int64_t D = s->D, first = s->sh[0].n0;
+  // a dense session keeps Xc = X - mean resident; hand back X (equal to the input up to one rounding)
+  if (s->centred) GP_TRY(dense_centre(s, +1.0));
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     const int64_t ch = std::min(chunk_obs(D), sh.n);
@@ -279,6 +283,7 @@ int gplvm_session_read_data(gplvm_ppca_session* s, double* Y, int64_t ld) {
     }
     CUDA_TRY(cudaFree(stage));
   }
+  if (s->centred) GP_TRY(dense_centre(s, -1.0));
   return GPLVM_OK;
 }
 
@@ -296,6 +301,7 @@ int gplvm_session_synth(gplvm_ppca_session* s, uint64_t seed, double nan_prob) {
   }
   s->has_data = true;
   s->initialised = false;
+  s->centred = false;
   return GPLVM_OK;
 }
 
