@@ -139,6 +139,28 @@ def dense_loglik(Xc: np.ndarray, W: np.ndarray, sigma2: float, literal_det: bool
     return -1.0 * (n / 2.0) * (d * math.log(2 * math.pi) + logdet + tr)
 
 
+def dense_stats(Xc: np.ndarray, W: np.ndarray, sigma2: float) -> np.ndarray:
+    """Per-shard statistics of one dense E-step (appendix A.1; additive over row shards of the CENTRED data):
+    packed [XEz (D x M) | Ez Ez^T (M x M)]."""
+    inv_m = np.linalg.inv(map_diagonal_add(W.T @ W, sigma2))
+    ez = inv_m @ (W.T @ Xc)
+    return np.concatenate([(Xc @ ez.T).ravel(), (ez @ ez.T).ravel()])
+
+
+def dense_update_from_stats(packed: np.ndarray, total_sum: float, n_total: int, W: np.ndarray, sigma2: float):
+    """Replicated M-step of appendix A.1 from the all-reduced statistics; total_sum = |Xc|_F^2 (all shards)."""
+    d, m = W.shape
+    xez = packed[:d * m].reshape(d, m)
+    ee = packed[d * m:].reshape(m, m)
+    inv_m = np.linalg.inv(map_diagonal_add(W.T @ W, sigma2))
+    ezz = (n_total * sigma2) * inv_m + ee
+    new_w = xez @ np.linalg.inv(ezz)
+    second = 2.0 * float(np.sum(new_w * xez))
+    third = float(np.sum((new_w @ _chol_upper(ezz).T) ** 2))
+    new_var = (total_sum - second + third) / float(n_total * d)
+    return new_w, new_var, max(0.0, float(np.max(np.abs(W - new_w)))), abs(new_var - sigma2)
+
+
 def _continue(stop: Stop, iteration: int, diff_var: float, max_diff_w: float) -> bool:
     """PPCA.hs:90-92 / :173-181."""
     kind, val = stop
@@ -270,22 +292,27 @@ def em_steps_missed(Y: np.ndarray, W0: np.ndarray, sigma2_0: float, stop: Stop,
 # missed_step_literal in tests/test_oracle.py; it is still an oracle (CPU, NumPy), not the product.
 # ----------------------------------------------------------------------------------------------
 
-def missed_step_vectorised(Y: np.ndarray, mu: np.ndarray, W: np.ndarray, sigma2: float,
-                           chunk: int = 8192):
+def missed_constants(Y: np.ndarray):
+    """Data constants of appendix A.3 (sums over observations => additive over row shards):
+    packed [n_d | sy_d | syy_d]."""
+    obs = ~np.isnan(Y)
+    y0 = np.where(obs, Y, 0.0)
+    return np.concatenate([obs.sum(axis=1).astype(np.float64), y0.sum(axis=1), (y0 * y0).sum(axis=1)])
+
+
+def missed_stats(Y: np.ndarray, mu: np.ndarray, W: np.ndarray, sigma2: float, chunk: int = 8192):
+    """Per-shard sufficient statistics of one masked E-step (additive over row shards), packed as
+    [S1 (D x M) | S2 (D x M) | G (D x M x M) | sum_i ez_i (M)], plus the shard's EX (M x n)."""
     d, n = Y.shape
     m = W.shape[1]
-    obs = ~np.isnan(Y)                                   # D x N
+    obs = ~np.isnan(Y)
     y0 = np.where(obs, Y, 0.0)
-    n_d = obs.sum(axis=1).astype(np.float64)
-    sy = y0.sum(axis=1)
-    syy = (y0 * y0).sum(axis=1)
-    kk = float(obs.sum())
     EX = np.empty((m, n))
     S1 = np.zeros((d, m)); S2 = np.zeros((d, m)); G = np.zeros((d, m, m))
-    ww = W[:, :, None] * W[:, None, :]                  # D x M x M outer products
+    ww = W[:, :, None] * W[:, None, :]
     for c0 in range(0, n, chunk):
         c1 = min(n, c0 + chunk)
-        o = obs[:, c0:c1].astype(np.float64)            # D x n
+        o = obs[:, c0:c1].astype(np.float64)
         Mi = np.einsum("dn,dab->nab", o, ww) + sigma2 * np.eye(m)
         b = np.einsum("dn,da->na", o * (y0[:, c0:c1] - mu[:, None]), W)
         Minv = np.linalg.inv(Mi)
@@ -295,6 +322,18 @@ def missed_step_vectorised(Y: np.ndarray, mu: np.ndarray, W: np.ndarray, sigma2:
         S1 += o @ ez
         S2 += (o * y0[:, c0:c1]) @ ez
         G += np.einsum("dn,nab->dab", o, A)
+    packed = np.concatenate([S1.ravel(), S2.ravel(), G.ravel(), EX.sum(axis=1)])
+    return packed, EX
+
+
+def missed_update_from_stats(packed: np.ndarray, consts: np.ndarray, W: np.ndarray, sigma2: float):
+    """Replicated M-step of appendix A.3 from the (all-reduced) statistics and data constants."""
+    d, m = W.shape
+    S1 = packed[:d * m].reshape(d, m)
+    S2 = packed[d * m:2 * d * m].reshape(d, m)
+    G = packed[2 * d * m:2 * d * m + d * m * m].reshape(d, m, m)
+    n_d, sy, syy = consts[:d], consts[d:2 * d], consts[2 * d:3 * d]
+    kk = float(n_d.sum())
     new_mu = (sy - np.einsum("da,da->d", W, S1)) / n_d
     r = S2 - new_mu[:, None] * S1
     new_w = np.linalg.solve(G, r[:, :, None])[:, :, 0]
@@ -303,9 +342,14 @@ def missed_step_vectorised(Y: np.ndarray, mu: np.ndarray, W: np.ndarray, sigma2:
     new_var = float(np.sum(c - 2 * np.einsum("da,da->d", new_w, r) + quad) / kk)
     max_diff_w = max(0.0, float(np.max(np.abs(W - new_w))))
     diff_var = abs(new_var - sigma2)
-    known = None
-    estep = dict(EX=EX, known=known)
-    return new_mu, new_w, new_var, max_diff_w, diff_var, estep
+    return new_mu, new_w, new_var, max_diff_w, diff_var
+
+
+def missed_step_vectorised(Y: np.ndarray, mu: np.ndarray, W: np.ndarray, sigma2: float,
+                           chunk: int = 8192):
+    packed, EX = missed_stats(Y, mu, W, sigma2, chunk)
+    new_mu, new_w, new_var, max_diff_w, diff_var = missed_update_from_stats(packed, missed_constants(Y), W, sigma2)
+    return new_mu, new_w, new_var, max_diff_w, diff_var, dict(EX=EX, known=None)
 
 
 def missed_loglik_vectorised(Y, new_mu, new_w, new_var, chunk: int = 8192) -> float:
