@@ -30,13 +30,9 @@ __device__ __forceinline__ double row_value(const double* __restrict__ X, int64_
     if (r < D) return X[n * ldx + r];
     return Ez[n * ldez + (r - D)];
   } else {
-    // rows: [0,D) observed flag | [D,2D) observed value | 2D: ones
-    if (r < D) return isnan(X[n * ldx + r]) ? 0.0 : 1.0;
-    if (r < 2 * D) {
-      const double v = X[n * ldx + (r - D)];
-      return isnan(v) ? 0.0 : v;
-    }
-    return 1.0;
+    // rows: [0,D) observed value, missing (NaN) -> 0
+    const double v = X[n * ldx + r];
+    return isnan(v) ? 0.0 : v;
   }
 }
 
@@ -335,13 +331,14 @@ int splits_for(int64_t n_obs, int64_t unit, int tiles_xy) {
 
 }  // namespace
 
-int launch_reduce_partials(ShardState& sh, int64_t S, int nparts) {
-  GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 256), 256, 0, sh.st, sh.partials, sh.stats, S, nparts, sh.par.scal);
+int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst) {
+  GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 256), 256, 0, sh.st, sh.partials, dst ? dst : sh.stats, S, nparts,
+            sh.par.scal);
   return GPLVM_OK;
 }
 
 int launch_stats_gemm(ShardState& sh, RowKind kind, int D, int R1, int R, int Q1, int Q2, const double* Cmat, int ldc,
-                      int Cw1, const double* Cmat2, int ldc2, int64_t S) {
+                      int Cw1, const double* Cmat2, int ldc2, int64_t S, double* dst) {
   const int rt = (int)ceil_div(R, TG_R), qt = (int)ceil_div(Q1, TG_Q);
   int ks = splits_for(sh.n, 1024, rt * qt);
   if (ks > sh.nparts) ks = sh.nparts;
@@ -353,9 +350,9 @@ int launch_stats_gemm(ShardState& sh, RowKind kind, int D, int R1, int R, int Q1
     GP_LAUNCH(stats_gemm_kernel<ROWS_DENSE>, grid, 256, 0, sh.st, sh.X, sh.ldx, sh.n, D, sh.par.MP, R1, R, Q1, Q2, Cmat, ldc,
               Cw1, Cmat2, ldc2, sh.partials, S, per, sh.par.scal);
   else
-    GP_LAUNCH(stats_gemm_kernel<ROWS_MASKED>, grid, 256, 0, sh.st, sh.X, sh.ldx, sh.n, D, sh.par.MP, R1, R, Q1, Q2, Cmat, ldc,
+    GP_LAUNCH(stats_gemm_kernel<ROWS_MASKED_VALUES>, grid, 256, 0, sh.st, sh.X, sh.ldx, sh.n, D, sh.par.MP, R1, R, Q1, Q2, Cmat, ldc,
               Cw1, Cmat2, ldc2, sh.partials, S, per, sh.par.scal);
-  GP_TRY(launch_reduce_partials(sh, S, ks));
+  GP_TRY(launch_reduce_partials(sh, S, ks, dst));
   return GPLVM_OK;
 }
 
@@ -419,7 +416,7 @@ static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double*
   const size_t smem = sizeof(double) * (64 * MP + 32 * 65);
   GP_LAUNCH(dense_ez_kernel, (unsigned)ceil_div(sh.n, 32), 256, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, proj, sh.Ez);
   const int R = D + MP;
-  return launch_stats_gemm(sh, ROWS_DENSE, D, R, R, MP, MP, sh.Ez, MP, MP, nullptr, 0, s->S);
+  return launch_stats_gemm(sh, ROWS_DENSE, D, R, R, MP, MP, sh.Ez, MP, MP, nullptr, 0, s->S, sh.stats);
 }
 
 int dense_enqueue_step(gplvm_ppca_session* s) {

@@ -22,9 +22,8 @@
 //   EE     : the B fragments of step 2 are also the A fragments of Ez^T . Ez; warp q handles k-step q.
 // Every partial result is written per CTA and summed over CTAs in fixed order by reduce_partials_kernel
 // (deterministic: the Haskell signature above this library is pure).
-#include <cuda.h>
-
 #include "ppca.cuh"
+#include "tma.cuh"
 
 namespace gplvm {
 namespace {
@@ -44,53 +43,27 @@ struct Cfg {
   static constexpr int MT2 = FW / 8;                // m-tiles per warp in step 2
   static constexpr int TPART_BYTES = NW * RT * EZ_LD * 8;
   static constexpr int EZ_BYTES = RT * EZ_LD * 8;
-  static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + TPART_BYTES + EZ_BYTES + 64;
+  static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + TPART_BYTES + 2 * EZ_BYTES + 64 + NW * RT * 8;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ double lds64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
-}
+enum StatsMode {
+  MODE_DENSE = 0,      // Ez = Xc proj ; XEz += Xc^T Ez ; EE += Ez^T Ez                       (dense EM step / dense LL pass)
+  MODE_MASKED_B = 1,   // b_i = sum_{d observed} w_d (y_id - mu_d), yy_i = sum_{d obs} (y_id - mu_d)^2 -> HBM (PPCA.hs:117)
+  MODE_MASKED_S2 = 2   // S2 += X0^T Ez with X0 = Y, NaN -> 0 and Ez read from HBM             (PPCA.hs:136)
+};
 
-// proj: D x 16 row-major projection (A = W Minv for the E-step, W for the log-likelihood pass)
-// partials: gridDim.x x S doubles; per CTA [XEz D x 16 | EE 16 x 16]
-template <int DD>
+// proj     : D x 16 row-major projection (DENSE: A = W Minv or W; MASKED_B: W)
+// partials : gridDim.x x S doubles; per CTA [XEz D x 16 | EE 16 x 16] (DENSE) or [S2 D x 16] (MASKED_S2)
+// mu       : D feature means (MASKED_B)         bout / yyout : n x 16 / n outputs of MASKED_B
+// ezsrc    : E[z_i] rows with leading dimension ldez (MASKED_S2)
+template <int DD, int MODE>
 __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                      const double* __restrict__ proj, int64_t n_obs,
                                                                      int64_t tiles_per_cta, double* __restrict__ partials,
-                                                                     int64_t S, const double* __restrict__ scal) {
+                                                                     int64_t S, const double* __restrict__ scal,
+                                                                     const double* __restrict__ mu, double* __restrict__ bout,
+                                                                     double* __restrict__ yyout, const double* __restrict__ ezsrc,
+                                                                     int64_t ldez) {
   using C = Cfg<DD>;
   if (scal[S_DONE] != 0.0) return;
   extern __shared__ uint8_t smem_raw[];
@@ -98,9 +71,10 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t tpart_u = base + C::STAGES * C::STAGE_BYTES;
   const uint32_t ez_u = tpart_u + C::TPART_BYTES;
-  const uint32_t bar_u = ez_u + C::EZ_BYTES;
+  const uint32_t bar_u = ez_u + 2 * C::EZ_BYTES;
   double* tpart = reinterpret_cast<double*>(gen_base + C::STAGES * C::STAGE_BYTES);
-  double* ezs = reinterpret_cast<double*>(gen_base + C::STAGES * C::STAGE_BYTES + C::TPART_BYTES);
+  double* ezs = reinterpret_cast<double*>(gen_base + C::STAGES * C::STAGE_BYTES + C::TPART_BYTES);  // 2 buffers
+  double* yys = reinterpret_cast<double*>(gen_base + C::STAGES * C::STAGE_BYTES + C::TPART_BYTES + 2 * C::EZ_BYTES + 64);
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -132,15 +106,22 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
   }
 
   // step-1 A^T fragments: proj[feature = w FW + 4 ks + t][latent = 8 mt + g], resident for the whole kernel
-  double preg[C::KS1][2];
+  constexpr int NP = (MODE == MODE_MASKED_S2) ? 1 : C::KS1;
+  double preg[NP][2];
+  double mureg[(MODE == MODE_MASKED_B) ? C::KS1 : 1];
+  if (MODE != MODE_MASKED_S2) {
 #pragma unroll
-  for (int ks = 0; ks < C::KS1; ++ks)
+    for (int ks = 0; ks < NP; ++ks) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) preg[ks][mt] = proj[(size_t)(w * C::FW + ks * 4 + t) * MPF + mt * 8 + g];
+      for (int mt = 0; mt < 2; ++mt) preg[ks][mt] = proj[(size_t)(w * C::FW + ks * 4 + t) * MPF + mt * 8 + g];
+      if (MODE == MODE_MASKED_B) mureg[ks] = mu[w * C::FW + ks * 4 + t];
+    }
+  }
 
-  double acc[C::MT2][2][2];  // XEz[feature = w FW + 8 mt + g][latent = 8 nt + 2 t + {0,1}]
+  constexpr int NA = (MODE == MODE_MASKED_B) ? 1 : C::MT2;
+  double acc[NA][2][2];  // XEz[feature = w FW + 8 mt + g][latent = 8 nt + 2 t + {0,1}]
 #pragma unroll
-  for (int mt = 0; mt < C::MT2; ++mt)
+  for (int mt = 0; mt < NA; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
   double ee[2][2][2];        // EE[8 a + g][8 b + 2 t + {0,1}] (this warp's k-steps only)
@@ -157,72 +138,130 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
   const uint32_t s2_thr = (uint32_t)(t * 256 + (g & 1) * 8);
   const uint32_t pg4 = (uint32_t)((((g >> 1) ^ (t << 1)) & 7) << 4);
   const uint32_t ez_thr = ez_u + (uint32_t)((t * 2 * EZ_LD + g) * 8);
+  const int rrow = tid >> 3, rlp = (tid & 7) * 2;  // (row, latent pair) of the reduce / Ez staging role
+
+  double2 eznext = make_double2(0.0, 0.0);
+  if (MODE == MODE_MASKED_S2 && ntiles > 0) {
+    const int64_t r = tile0 * RT + rrow;
+    if (r < n_obs) eznext = *reinterpret_cast<const double2*>(&ezsrc[r * ldez + rlp]);
+  }
 
   for (int64_t i = 0; i < ntiles; ++i) {
     const int s = (int)(i % C::STAGES);
     const uint32_t xs = base + s * C::STAGE_BYTES;
-    mbar_wait(bar_u + 8 * s, (uint32_t)((i / C::STAGES) & 1));
+    uint32_t ezbuf_off = 0;
 
-    // ---- step 1: partial T^T (16 latent x 16 rows) over this warp's feature slice ---------------------
-    double tp[2][2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) tp[mt][nt][0] = tp[mt][nt][1] = 0.0;
-#pragma unroll
-    for (int ks = 0; ks < C::KS1; ++ks) {
-      const int f = w * C::FW + ks * 4;  // w is warp-uniform: the chunk offset is a runtime add, the rest folds
-      const uint32_t chunk_off = (uint32_t)((f >> 4) * (RT * 128));
-      const uint32_t u0 = (uint32_t)(((ks * 4) & 15) >> 1) << 4;  // FW % 16 == 0 => (f & 15) == (4 ks & 15)
-      const uint32_t a0 = xs + chunk_off + s1_thr + (u0 ^ gx4);
-      const double x0 = lds64(a0);
-      const double x1 = lds64(a0 + 1024);
-      dmma(tp[0][0], preg[ks][0], x0);
-      dmma(tp[1][0], preg[ks][1], x0);
-      dmma(tp[0][1], preg[ks][0], x1);
-      dmma(tp[1][1], preg[ks][1], x1);
-    }
-    // tp[mt][nt][c] = T[row 8 nt + 2 t + c][latent 8 mt + g]  -> tpart[w][row][latent]
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tpart[(w * RT + nt * 8 + 2 * t + c) * EZ_LD + mt * 8 + g] = tp[mt][nt][c];
-    __syncthreads();  // S1: partials complete; every warp is also done with step 2 of the previous tile
-
-    if (tid == 0 && i >= 1 && i - 1 + C::STAGES < ntiles) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(i - 1 + C::STAGES);
-    }
-    {  // fixed-order sum of the 4 partials: thread -> (row, latent pair)
-      const int row = tid >> 3, lp = (tid & 7) * 2;
-      double2 sacc = *reinterpret_cast<const double2*>(&tpart[(0 * RT + row) * EZ_LD + lp]);
-#pragma unroll
-      for (int q = 1; q < NW; ++q) {
-        const double2 v = *reinterpret_cast<const double2*>(&tpart[(q * RT + row) * EZ_LD + lp]);
-        sacc.x += v.x;
-        sacc.y += v.y;
+    if (MODE == MODE_MASKED_S2) {
+      // Ez tile of this stage from HBM (prefetched one tile ahead); double-buffered => one CTA barrier per tile
+      ezbuf_off = (uint32_t)((i & 1) * C::EZ_BYTES);
+      *reinterpret_cast<double2*>(&ezs[(i & 1) * (RT * EZ_LD) + rrow * EZ_LD + rlp]) = eznext;
+      eznext = make_double2(0.0, 0.0);
+      if (i + 1 < ntiles) {
+        const int64_t r = (tile0 + i + 1) * RT + rrow;
+        if (r < n_obs) eznext = *reinterpret_cast<const double2*>(&ezsrc[r * ldez + rlp]);
       }
-      *reinterpret_cast<double2*>(&ezs[row * EZ_LD + lp]) = sacc;
+      mbar_wait(bar_u + 8 * s, (uint32_t)((i / C::STAGES) & 1));
+      __syncthreads();  // Ez tile visible; every warp is done with step 2 of the previous tile
+      if (tid == 0 && i >= 1 && i - 1 + C::STAGES < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(i - 1 + C::STAGES);
+      }
+    } else {
+      mbar_wait(bar_u + 8 * s, (uint32_t)((i / C::STAGES) & 1));
+
+      // ---- step 1: partial T^T (16 latent x 16 rows) over this warp's feature slice -------------------
+      double tp[2][2][2];
+      double yacc0 = 0.0, yacc1 = 0.0;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) tp[mt][nt][0] = tp[mt][nt][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < C::KS1; ++ks) {
+        const int f = w * C::FW + ks * 4;  // w is warp-uniform: the chunk offset is a runtime add, the rest folds
+        const uint32_t chunk_off = (uint32_t)((f >> 4) * (RT * 128));
+        const uint32_t u0 = (uint32_t)(((ks * 4) & 15) >> 1) << 4;  // FW % 16 == 0 => (f & 15) == (4 ks & 15)
+        const uint32_t a0 = xs + chunk_off + s1_thr + (u0 ^ gx4);
+        double x0 = lds64(a0);
+        double x1 = lds64(a0 + 1024);
+        if (MODE == MODE_MASKED_B) {  // missing -> 0, observed -> y - mu   (PPCA.hs:112-113,117)
+          x0 = (x0 == x0) ? x0 - mureg[ks] : 0.0;
+          x1 = (x1 == x1) ? x1 - mureg[ks] : 0.0;
+          yacc0 = fma(x0, x0, yacc0);
+          yacc1 = fma(x1, x1, yacc1);
+        }
+        dmma(tp[0][0], preg[ks][0], x0);
+        dmma(tp[1][0], preg[ks][1], x0);
+        dmma(tp[0][1], preg[ks][0], x1);
+        dmma(tp[1][1], preg[ks][1], x1);
+      }
+      // tp[mt][nt][c] = T[row 8 nt + 2 t + c][latent 8 mt + g]  -> tpart[w][row][latent]
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) tpart[(w * RT + nt * 8 + 2 * t + c) * EZ_LD + mt * 8 + g] = tp[mt][nt][c];
+      if (MODE == MODE_MASKED_B) {
+        yacc0 += __shfl_xor_sync(0xffffffffu, yacc0, 1);
+        yacc0 += __shfl_xor_sync(0xffffffffu, yacc0, 2);
+        yacc1 += __shfl_xor_sync(0xffffffffu, yacc1, 1);
+        yacc1 += __shfl_xor_sync(0xffffffffu, yacc1, 2);
+        if (t == 0) {
+          yys[w * RT + g] = yacc0;
+          yys[w * RT + 8 + g] = yacc1;
+        }
+      }
+      __syncthreads();  // S1: partials complete; every warp is also done with step 2 of the previous tile
+
+      if (MODE == MODE_MASKED_B) {  // step 1 was the only reader of this stage: re-arm it right away
+        if (tid == 0 && i + C::STAGES < ntiles) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(i + C::STAGES);
+        }
+      } else if (tid == 0 && i >= 1 && i - 1 + C::STAGES < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(i - 1 + C::STAGES);
+      }
+      {  // fixed-order sum of the 4 partials: thread -> (row, latent pair)
+        double2 sacc = *reinterpret_cast<const double2*>(&tpart[(0 * RT + rrow) * EZ_LD + rlp]);
+#pragma unroll
+        for (int q = 1; q < NW; ++q) {
+          const double2 v = *reinterpret_cast<const double2*>(&tpart[(q * RT + rrow) * EZ_LD + rlp]);
+          sacc.x += v.x;
+          sacc.y += v.y;
+        }
+        if (MODE == MODE_MASKED_B) {
+          const int64_t r = (tile0 + i) * RT + rrow;
+          if (r < n_obs) {
+            *reinterpret_cast<double2*>(&bout[r * MPF + rlp]) = sacc;
+            if (rlp == 0) yyout[r] = ((yys[rrow] + yys[RT + rrow]) + yys[2 * RT + rrow]) + yys[3 * RT + rrow];
+          }
+        } else {
+          *reinterpret_cast<double2*>(&ezs[rrow * EZ_LD + rlp]) = sacc;
+        }
+      }
+      __syncthreads();  // S2: Ez tile complete (MASKED_B: partial tiles free again)
     }
-    __syncthreads();  // S2: Ez tile complete
+
+    if (MODE == MODE_MASKED_B) continue;
 
     // ---- step 2: XEz += Xc^T . Ez ;  EE += Ez^T . Ez ----------------------------------------------------
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int rowc = 8 * (j >> 1) + (j & 1);  // rows rho(j, t) = rowc + 2 t
-      const double e0 = lds64(ez_thr + (uint32_t)((rowc * EZ_LD) * 8));
-      const double e1 = lds64(ez_thr + (uint32_t)((rowc * EZ_LD + 8) * 8));
+      const double e0 = lds64(ez_thr + ezbuf_off + (uint32_t)((rowc * EZ_LD) * 8));
+      const double e1 = lds64(ez_thr + ezbuf_off + (uint32_t)((rowc * EZ_LD + 8) * 8));
 #pragma unroll
-      for (int mt = 0; mt < C::MT2; ++mt) {
+      for (int mt = 0; mt < NA; ++mt) {
         const uint32_t chunk_off = (uint32_t)(((w * C::FW) >> 4) + (mt >> 1)) * (RT * 128);
         const uint32_t cc4 = (uint32_t)((((mt & 1) << 2) ^ (j & 1)) << 4);
-        const double xa = lds64(xs + chunk_off + (uint32_t)(rowc * 128) + s2_thr + (cc4 ^ pg4));
+        double xa = lds64(xs + chunk_off + (uint32_t)(rowc * 128) + s2_thr + (cc4 ^ pg4));
+        if (MODE == MODE_MASKED_S2) xa = (xa == xa) ? xa : 0.0;
         dmma(acc[mt][0], xa, e0);
         dmma(acc[mt][1], xa, e1);
       }
-      if (j == w) {
+      if (MODE == MODE_DENSE && j == w) {
         dmma(ee[0][0], e0, e0);
         dmma(ee[0][1], e0, e1);
         dmma(ee[1][0], e1, e0);
@@ -230,16 +269,18 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
       }
     }
   }
+  if (MODE == MODE_MASKED_B) return;
 
   // ---- epilogue: per-CTA partial statistics ---------------------------------------------------------------
   double* out = partials + (size_t)blockIdx.x * S;
 #pragma unroll
-  for (int mt = 0; mt < C::MT2; ++mt)
+  for (int mt = 0; mt < NA; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       const int f = w * C::FW + mt * 8 + g;
       *reinterpret_cast<double2*>(&out[(size_t)f * MPF + nt * 8 + 2 * t]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
     }
+  if (MODE != MODE_DENSE) return;
   __syncthreads();
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -257,56 +298,56 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct MaskedArgs {
+  const double* mu = nullptr;
+  double* bout = nullptr;
+  double* yyout = nullptr;
+  const double* ezsrc = nullptr;
+  int64_t ldez = 0;
+};
 
-int get_encode_fn(EncodeTiledFn* fn) {
-  static EncodeTiledFn cached = nullptr;
-  if (!cached) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
-    if (qres != cudaDriverEntryPointSuccess || !p) return fail(GPLVM_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-    cached = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  *fn = cached;
-  return GPLVM_OK;
-}
-
-template <int DD>
-int launch_dmma(ShardState& sh, const double* proj, int64_t S, int grid, int64_t tiles_per_cta) {
+template <int DD, int MODE>
+int launch_dmma(ShardState& sh, const double* proj, int64_t S, int grid, int64_t tiles_per_cta, const MaskedArgs& ma) {
   using C = Cfg<DD>;
   static bool attr_done[64] = {};
   if (!attr_done[sh.dev & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute(dense_stats_dmma_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(dense_stats_dmma_kernel<DD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute((dense_stats_dmma_kernel<DD, MODE>), cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    CUDA_TRY(cudaFuncSetAttribute((dense_stats_dmma_kernel<DD, MODE>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done[sh.dev & 63] = true;
   }
   const CUtensorMap* tm = static_cast<const CUtensorMap*>(sh.tmap);
-  GP_LAUNCH(dense_stats_dmma_kernel<DD>, grid, NW * 32, C::SMEM, sh.st, *tm, proj, sh.n, tiles_per_cta, sh.partials, S, sh.par.scal);
+  GP_LAUNCH((dense_stats_dmma_kernel<DD, MODE>), grid, NW * 32, C::SMEM, sh.st, *tm, proj, sh.n, tiles_per_cta, sh.partials, S,
+            sh.par.scal, ma.mu, ma.bout, ma.yyout, ma.ezsrc, ma.ldez);
   return GPLVM_OK;
 }
 
-int sm_count(int dev) {
-  static int cache[64] = {};
-  if (!cache[dev & 63]) cudaDeviceGetAttribute(&cache[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-  return cache[dev & 63] > 0 ? cache[dev & 63] : 148;
+template <int MODE>
+int dispatch_dmma(gplvm_ppca_session* s, ShardState& sh, const double* proj, int64_t S, const MaskedArgs& ma, int* grid_out) {
+  const int64_t ntiles = ceil_div(sh.n, RT);
+  int grid = (int)std::min<int64_t>(2 * sm_count(sh.dev), ntiles);
+  if (grid > sh.nparts) grid = sh.nparts;
+  const int64_t per = ceil_div(ntiles, grid);
+  grid = (int)ceil_div(ntiles, per);
+  if (grid_out) *grid_out = grid;
+  switch (s->D) {
+    case 64: return launch_dmma<64, MODE>(sh, proj, S, grid, per, ma);
+    case 128: return launch_dmma<128, MODE>(sh, proj, S, grid, per, ma);
+    case 256: return launch_dmma<256, MODE>(sh, proj, S, grid, per, ma);
+    default: return fail(GPLVM_ERR_STATE, "fused DMMA kernel: unsupported D");
+  }
 }
 
 }  // namespace
 
 bool dense_dmma_eligible(const gplvm_ppca_session* s) {
-  if (s->missing) return false;
   if (s->M > MPF) return false;
+  if (s->missing && s->M != MPF) return false;  // the fused masked solver is specialised for M = 16
   return s->D == 64 || s->D == 128 || s->D == 256;
 }
 
 int dense_dmma_nparts(const gplvm_ppca_session*, const ShardState& sh) { return 2 * sm_count(sh.dev); }
 
 int dense_dmma_prepare(gplvm_ppca_session* s) {
-  EncodeTiledFn enc = nullptr;
-  GP_TRY(get_encode_fn(&enc));
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (!sh.tmap) {
@@ -314,33 +355,32 @@ int dense_dmma_prepare(gplvm_ppca_session* s) {
       if (posix_memalign(&p, 128, sizeof(CUtensorMap)) != 0) return fail(GPLVM_ERR_CUDA, "out of host memory");
       sh.tmap = p;
     }
-    const cuuint64_t gdim[2] = {(cuuint64_t)s->D, (cuuint64_t)sh.n};
-    const cuuint64_t gstr[1] = {(cuuint64_t)sh.ldx * sizeof(double)};
-    const cuuint32_t box[2] = {16u, (cuuint32_t)RT};
-    const cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(static_cast<CUtensorMap*>(sh.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, sh.X, gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(GPLVM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    GP_TRY(encode_rows_map(static_cast<CUtensorMap*>(sh.tmap), sh.X, s->D, sh.n, sh.ldx, RT));
   }
   return GPLVM_OK;
 }
 
 int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj) {
-  const int64_t ntiles = ceil_div(sh.n, RT);
-  int grid = (int)std::min<int64_t>(2 * sm_count(sh.dev), ntiles);
-  if (grid > sh.nparts) grid = sh.nparts;
-  const int64_t per = ceil_div(ntiles, grid);
-  grid = (int)ceil_div(ntiles, per);
-  int rc;
-  switch (s->D) {
-    case 64: rc = launch_dmma<64>(sh, proj, s->S, grid, per); break;
-    case 128: rc = launch_dmma<128>(sh, proj, s->S, grid, per); break;
-    case 256: rc = launch_dmma<256>(sh, proj, s->S, grid, per); break;
-    default: return fail(GPLVM_ERR_STATE, "dense DMMA kernel: unsupported D");
-  }
-  GP_TRY(rc);
+  int grid = 0;
+  GP_TRY(dispatch_dmma<MODE_DENSE>(s, sh, proj, s->S, MaskedArgs(), &grid));
   return launch_reduce_partials(sh, s->S, grid);
+}
+
+// b_i = W_obs^T (y_i - mu)_obs and yy_i = |(y_i - mu)_obs|^2 for every local observation (masked E-step / masked LL)
+int masked_dmma_b(gplvm_ppca_session* s, ShardState& sh, const double* W, const double* mu, double* bout, double* yyout) {
+  MaskedArgs ma;
+  ma.mu = mu; ma.bout = bout; ma.yyout = yyout;
+  return dispatch_dmma<MODE_MASKED_B>(s, sh, W, 0, ma, nullptr);
+}
+
+// dst (D x 16) = sum_i (y_i, NaN -> 0) ez_i^T, ez_i = row i of `ez` (leading dimension ldez)
+int masked_dmma_s2(gplvm_ppca_session* s, ShardState& sh, const double* ez, int64_t ldez, double* dst) {
+  MaskedArgs ma;
+  ma.ezsrc = ez; ma.ldez = ldez;
+  int grid = 0;
+  const int64_t S = (int64_t)s->D * MPF;
+  GP_TRY(dispatch_dmma<MODE_MASKED_S2>(s, sh, nullptr, S, ma, &grid));
+  return launch_reduce_partials(sh, S, grid, dst);
 }
 
 int dense_dmma_release(gplvm_ppca_session*) { return GPLVM_OK; }

@@ -5,7 +5,9 @@
 //   M_i  = (s2 I + W^T W) - sum_{d missing} w_d w_d^T                                  (PPCA.hs:114-115)
 //   b_i  = sum_{d in O_i} w_d (y_id - mu_d);  ez_i = M_i^-1 b_i                         (PPCA.hs:116-117)
 //   A_i  = ez_i ez_i^T + s2 M_i^-1
-// statistics:  S1_d = sum_i o_id ez_i,  S2_d = sum_i o_id y_id ez_i,  G_d = sum_i o_id A_i,  sum_i ez_i
+// statistics (complement form: the work is proportional to the MISSING entries):
+//   tot = sum_i [vech A_i | ez_i],   miss_d = sum_{i : d missing} [vech A_i | ez_i],   S2_d = sum_i o_id y_id ez_i
+//   => G_d = tot_A - miss_d,A ;  S1_d = tot_ez - miss_d,ez
 // update (per feature d, replicated):
 //   mu'_d = (sy_d - w_d . S1_d) / n_d                                                   (PPCA.hs:123)
 //   r_d   = S2_d - mu'_d S1_d ;  w'_d = G_d^-1 r_d                                       (PPCA.hs:133-137)
@@ -114,12 +116,12 @@ __device__ __forceinline__ int masked_build(const double* __restrict__ x, const 
 
 // E-step: one warp per observation; writes ez_i (M) and vech(A_i) (NV) to HBM.
 __global__ void __launch_bounds__(EW * 32) masked_estep_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, Par p,
-                                                              double* __restrict__ Ez, double* __restrict__ Av) {
+                                                              double* __restrict__ EA, int eas) {
   if (p.scal[S_DONE] != 0.0) return;
   extern __shared__ double sm[];
   const int M = p.M, NV = p.NV;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double* Mi = sm + (size_t)w * (2 * M * M + 2 * M);
+  double* Mi = sm + (size_t)w * (2 * M * M + 3 * M);
   double* Inv = Mi + M * M;
   double* b = Inv + M * M;
   const double s2 = p.scal[S_SIGMA2];
@@ -129,8 +131,7 @@ __global__ void __launch_bounds__(EW * 32) masked_estep_kernel(const double* __r
     const int cnt = masked_build(X + n * ldx, p, Mi, b, lane, yy);
     if (cnt == 0) {
       if (lane == 0) set_err(p.scal, 2.0);
-      for (int a = lane; a < M; a += 32) Ez[n * M + a] = 0.0;
-      for (int e = lane; e < NV; e += 32) Av[n * NV + e] = 0.0;
+      for (int e = lane; e < eas; e += 32) EA[n * eas + e] = 0.0;
       continue;
     }  // all-NaN observation: unsupported (Util.hs:81)
     const bool ok = warp_cholesky(Mi, M, lane);
@@ -152,21 +153,132 @@ __global__ void __launch_bounds__(EW * 32) masked_estep_kernel(const double* __r
       }
     }
     __syncwarp();
-    for (int a = lane; a < M; a += 32) Ez[n * M + a] = b[a];
+    for (int a = lane; a < M; a += 32) EA[n * eas + NV + a] = b[a];
     // vech (row-wise lower triangle): index(a, c) = a (a+1)/2 + c, c <= a
     for (int e = lane; e < NV; e += 32) {
       int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
       while ((a + 1) * (a + 2) / 2 <= e) ++a;
       while (a * (a + 1) / 2 > e) --a;
       const int c = e - a * (a + 1) / 2;
-      Av[n * NV + e] = fma(b[a], b[c], s2 * Inv[a * M + c]);
+      EA[n * eas + e] = fma(b[a], b[c], s2 * Inv[a * M + c]);
     }
     __syncwarp();
   }
 }
 
-// per-feature update, one warp per feature.  stats layout:
-//   block 1: D rows x (M + NV): [S1_d | vech G_d];  block 2: D rows x M: S2_d; then one row sum_i ez_i
+// mbits[n][word] bit j = feature 32 word + j of observation n is missing (NaN); constant over the EM iterations
+__global__ void __launch_bounds__(256) masked_bits_kernel(const double* __restrict__ X, int64_t ldx, int64_t n_obs, int D, int wpr,
+                                                          uint32_t* __restrict__ mbits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= n_obs) return;
+  for (int wd = 0; wd < wpr; ++wd) {
+    const int d = wd * 32 + lane;
+    const bool miss = (d < D) && isnan(X[n * ldx + d]);
+    const unsigned m = __ballot_sync(0xffffffffu, miss);
+    if (lane == 0) mbits[n * wpr + wd] = m;
+  }
+}
+
+// Complement sums.  grid = (row blocks, feature groups); 8 warps per CTA; warp w of feature group fg owns the FPW
+// features f0 = (8 fg + w) FPW ... and keeps miss_d[e] for them in REGISTERS: lane l owns e = l + 32 k, k < KPL.
+// For every observation the warp loads its slice of [vech A_i | ez_i] once and adds it to the accumulators of the
+// features that observation misses (warp-uniform tests on the packed mask bits) -- work ~ #missing, fixed order
+// (rows ascending) => deterministic, no atomics.  Warp 0 of feature group 0 also accumulates the totals.
+// partials: [row block][(D + 1) x eas]  (row D = totals)
+template <int KPL, int FPW>
+__global__ void __launch_bounds__(256) masked_miss_sums_kernel(const double* __restrict__ EA, int eas, const uint32_t* __restrict__ mbits,
+                                                               int wpr, int64_t n_obs, int64_t rows_per_cta, int D,
+                                                               double* __restrict__ partials, int64_t Spart,
+                                                               const double* __restrict__ scal) {
+  if (scal[S_DONE] != 0.0) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int f0 = ((int)blockIdx.y * 8 + w) * FPW;
+  const bool totals = (blockIdx.y == 0 && w == 0);
+  if (f0 >= D && !totals) return;
+  double acc[FPW][KPL], tot[KPL];
+#pragma unroll
+  for (int f = 0; f < FPW; ++f)
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) acc[f][k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < KPL; ++k) tot[k] = 0.0;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(n_obs, r0 + rows_per_cta);
+  const int word = f0 >> 5, shift = f0 & 31;
+  const unsigned fmask = (FPW >= 32) ? 0xffffffffu : ((1u << FPW) - 1u);
+  const bool has_feat = f0 < D;
+  int64_t r = r0;
+  for (; r + 1 < r1; r += 2) {  // two observations in flight
+    double a0[KPL], a1[KPL];
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int e = lane + 32 * k;
+      a0[k] = (e < eas) ? EA[r * eas + e] : 0.0;
+      a1[k] = (e < eas) ? EA[(r + 1) * eas + e] : 0.0;
+    }
+    const unsigned m0 = has_feat ? ((mbits[r * wpr + word] >> shift) & fmask) : 0u;
+    const unsigned m1 = has_feat ? ((mbits[(r + 1) * wpr + word] >> shift) & fmask) : 0u;
+    if (totals) {
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) tot[k] += a0[k];
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) tot[k] += a1[k];
+    }
+#pragma unroll
+    for (int f = 0; f < FPW; ++f) {
+      if (m0 & (1u << f)) {
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) acc[f][k] += a0[k];
+      }
+      if (m1 & (1u << f)) {
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) acc[f][k] += a1[k];
+      }
+    }
+  }
+  for (; r < r1; ++r) {
+    double a0[KPL];
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int e = lane + 32 * k;
+      a0[k] = (e < eas) ? EA[r * eas + e] : 0.0;
+    }
+    const unsigned m0 = has_feat ? ((mbits[r * wpr + word] >> shift) & fmask) : 0u;
+    if (totals) {
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) tot[k] += a0[k];
+    }
+#pragma unroll
+    for (int f = 0; f < FPW; ++f)
+      if (m0 & (1u << f)) {
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) acc[f][k] += a0[k];
+      }
+  }
+  double* out = partials + (int64_t)blockIdx.x * Spart;
+  if (has_feat) {
+#pragma unroll
+    for (int f = 0; f < FPW; ++f) {
+      if (f0 + f >= D) break;
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) {
+        const int e = lane + 32 * k;
+        if (e < eas) out[(int64_t)(f0 + f) * eas + e] = acc[f][k];
+      }
+    }
+  }
+  if (totals) {
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int e = lane + 32 * k;
+      if (e < eas) out[(int64_t)D * eas + e] = tot[k];
+    }
+  }
+}
+
+// per-feature update, one warp per feature.  stats layout (all-reduced):
+//   [miss_d = (vech G^miss_d | S1^miss_d) : D x eas] [tot = (vech sum A | sum ez) : eas] [S2_d : D x M]
 __global__ void __launch_bounds__(EW * 32) masked_update_kernel(Par p, const double* __restrict__ stats, double* __restrict__ scratch) {
   if (p.scal[S_DONE] != 0.0) return;
   extern __shared__ double sm[];
@@ -174,19 +286,24 @@ __global__ void __launch_bounds__(EW * 32) masked_update_kernel(Par p, const dou
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int d = blockIdx.x * EW + w;
   if (d >= D) return;
-  double* G = sm + (size_t)w * (2 * M * M + 2 * M);
+  double* G = sm + (size_t)w * (2 * M * M + 3 * M);
   double* G0 = G + M * M;
   double* r = G0 + M * M;
   double* wold = r + M;
-  const double* S1 = stats + (int64_t)d * (M + NV);
-  const double* Gv = S1 + M;
-  const double* S2 = stats + (int64_t)D * (M + NV) + (int64_t)d * M;
+  const int eas = NV + M;
+  const double* miss = stats + (int64_t)d * eas;
+  const double* tot = stats + (int64_t)D * eas;
+  const double* S2 = stats + (int64_t)(D + 1) * eas + (int64_t)d * M;
+  double* S1 = wold + M;  // M doubles of per-warp scratch (see warp_scratch_bytes)
   for (int e = lane; e < M * M; e += 32) {
     const int a = e / M, c = e % M;
-    const double v = (c <= a) ? Gv[a * (a + 1) / 2 + c] : Gv[c * (c + 1) / 2 + a];
+    const int v_idx = (c <= a) ? a * (a + 1) / 2 + c : c * (c + 1) / 2 + a;
+    const double v = tot[v_idx] - miss[v_idx];
     G[e] = v;
     G0[e] = v;
   }
+  for (int a = lane; a < M; a += 32) S1[a] = tot[NV + a] - miss[NV + a];
+  __syncwarp();
   double dot = 0.0;
   for (int a = lane; a < M; a += 32) {
     wold[a] = p.W[(int64_t)d * M + a];
@@ -255,7 +372,7 @@ __global__ void __launch_bounds__(256) masked_finalize_kernel(Par p, const doubl
   a = block_sum(a, red);
   m = block_max(m, red);
   // mean of the E-step latent means, needed by the restore (meanColumn expX^T, PPCA.hs:162)
-  const double* sez = stats + (int64_t)D * (M + NV) + (int64_t)D * M;
+  const double* sez = stats + (int64_t)D * (NV + M) + NV;
   for (int b = threadIdx.x; b < M; b += blockDim.x) p.c[b] = sez[b] / (double)p.N;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -298,7 +415,7 @@ __global__ void __launch_bounds__(EW * 32) masked_ll_kernel(const double* __rest
   __shared__ double wsum[EW];
   const int M = p.M;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double* Mi = sm + (size_t)w * (2 * M * M + 2 * M);
+  double* Mi = sm + (size_t)w * (2 * M * M + 3 * M);
   double* b = Mi + 2 * M * M;
   const double s2 = p.scal[S_SIGMA2];
   const double log2pi = log(2.0 * M_PI), logs2 = log(s2);
@@ -370,13 +487,13 @@ __global__ void __launch_bounds__(256) masked_restore_prep_kernel(Par p, double*
 }
 
 // out[d][i] = B_d . ez_i + fm_d for a chunk of observations; out is feature-major (D x ld)
-__global__ void __launch_bounds__(256) masked_restore_kernel(Par p, const double* __restrict__ Ez, const double* __restrict__ fm,
+__global__ void __launch_bounds__(256) masked_restore_kernel(Par p, const double* __restrict__ Ez, int ldez, const double* __restrict__ fm,
                                                             double* __restrict__ out, int64_t ld, int64_t n_chunk) {
   const int M = p.M, D = p.D;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double ez[GPLVM_MAX_M];
   if (i < n_chunk)
-    for (int a = 0; a < M; ++a) ez[a] = Ez[i * M + a];
+    for (int a = 0; a < M; ++a) ez[a] = Ez[i * ldez + a];
   for (int d = 0; d < D; ++d) {
     if (i < n_chunk) {
       double t = fm[d];
@@ -386,11 +503,15 @@ __global__ void __launch_bounds__(256) masked_restore_kernel(Par p, const double
   }
 }
 
-size_t warp_scratch_bytes(int M) { return sizeof(double) * (size_t)EW * (2 * M * M + 2 * M); }
+size_t warp_scratch_bytes(int M) { return sizeof(double) * (size_t)EW * (2 * M * M + 3 * M); }
 
 }  // namespace
 
 int masked_init_constants(gplvm_ppca_session* s) {
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(masked_bits_kernel, (unsigned)ceil_div(sh.n, 8), 256, 0, sh.st, sh.X, sh.ldx, sh.n, (int)s->D, s->WPR, sh.mbits);
+  }
   GP_TRY(moments_pass(s, 2));
   GP_TRY(session_allreduce_stats(s, 3 * s->D));
   for (ShardState& sh : s->sh) {
@@ -411,15 +532,45 @@ int masked_init_constants(gplvm_ppca_session* s) {
   return GPLVM_OK;
 }
 
+static int launch_miss_sums(gplvm_ppca_session* s, ShardState& sh) {
+  const int D = (int)s->D, eas = s->EAS;
+  const int64_t Spart = (int64_t)(D + 1) * eas;
+  const bool small = eas <= 160;   // M <= 16: 5 values per lane, 16 features per warp; else 18 per lane, 2 features
+  const int fpw = small ? 16 : 2;
+  const int fgroups = (int)ceil_div(D, 8 * fpw);
+  int rb = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * 148) / fgroups), sh.nparts);
+  const int64_t rows_per_cta = std::max<int64_t>(ceil_div(sh.n, rb), 2);
+  rb = (int)ceil_div(sh.n, rows_per_cta);
+  dim3 grid(rb, fgroups);
+  if (small)
+    GP_LAUNCH((masked_miss_sums_kernel<5, 16>), grid, 256, 0, sh.st, sh.EA, eas, sh.mbits, s->WPR, sh.n, rows_per_cta, D, sh.partials,
+              Spart, sh.par.scal);
+  else
+    GP_LAUNCH((masked_miss_sums_kernel<18, 2>), grid, 256, 0, sh.st, sh.EA, eas, sh.mbits, s->WPR, sh.n, rows_per_cta, D, sh.partials,
+              Spart, sh.par.scal);
+  return launch_reduce_partials(sh, Spart, rb, sh.stats);
+}
+
 int masked_enqueue_step(gplvm_ppca_session* s) {
-  const int M = (int)s->M, NV = s->NV, D = (int)s->D;
+  const int M = (int)s->M, D = (int)s->D;
   const size_t smem = warp_scratch_bytes(M);
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (sh.evk0) CUDA_TRY(cudaEventRecord(sh.evk0, sh.st));
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(sh.n, EW), 148 * 8);
-    GP_LAUNCH(masked_estep_kernel, grid, EW * 32, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, sh.Ez, sh.Av);
-    GP_TRY(launch_stats_gemm(sh, ROWS_MASKED, D, D, 2 * D + 1, M + NV, M, sh.Ez, M, M, sh.Av, NV, s->S));
+    double* s2dst = sh.stats + (int64_t)(D + 1) * s->EAS;
+    if (s->use_dmma) {
+      // fused path (M = 16): b_i by TMA + DMMA, per-observation register solver, sparse complement sums, S2 by DMMA
+      GP_TRY(masked_dmma_b(s, sh, sh.par.W, sh.par.mu, sh.Ez, sh.yy));
+      GP_TRY(masked_fused_solve(s, sh, sh.Ez, sh.yy, false, nullptr));
+      GP_TRY(launch_miss_sums(s, sh));
+      GP_TRY(masked_dmma_s2(s, sh, sh.EA + s->NV, s->EAS, s2dst));
+    } else {
+      const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(sh.n, EW), 148 * 8);
+      GP_LAUNCH(masked_estep_kernel, grid, EW * 32, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, sh.EA, s->EAS);
+      GP_TRY(launch_miss_sums(s, sh));
+      // S2_d = sum_i o_id y_id ez_i  (D x M)
+      GP_TRY(launch_stats_gemm(sh, ROWS_MASKED_VALUES, D, D, D, M, M, sh.EA + s->NV, s->EAS, M, nullptr, 0, (int64_t)D * M, s2dst));
+    }
     if (sh.evk1) CUDA_TRY(cudaEventRecord(sh.evk1, sh.st));
   }
   GP_TRY(session_allreduce_stats(s, s->S));
@@ -435,10 +586,16 @@ int masked_loglik(gplvm_ppca_session* s, double* ll) {
   const size_t smem = warp_scratch_bytes((int)s->M);
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(sh.n, EW), (int64_t)sh.nparts);
-    GP_LAUNCH(masked_ll_kernel, grid, EW * 32, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, sh.partials);
+    int grid = 0;
+    if (s->use_dmma) {
+      GP_TRY(masked_dmma_b(s, sh, sh.par.W, sh.par.mu, sh.Ez, sh.yy));
+      GP_TRY(masked_fused_solve(s, sh, sh.Ez, sh.yy, true, &grid));
+    } else {
+      grid = (int)std::min<int64_t>(ceil_div(sh.n, EW), (int64_t)sh.nparts);
+      GP_LAUNCH(masked_ll_kernel, (unsigned)grid, EW * 32, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, sh.partials);
+    }
     // partials are 1 double per CTA: reduce with S = 1
-    GP_TRY(launch_reduce_partials(sh, 1, (int)grid));
+    GP_TRY(launch_reduce_partials(sh, 1, grid));
   }
   GP_TRY(session_allreduce_stats(s, 1));
   for (ShardState& sh : s->sh) {
@@ -471,7 +628,8 @@ int masked_restore(gplvm_ppca_session* s, double* restored, int64_t ld) {
     CUDA_TRY(cudaMalloc(&stage, sizeof(double) * (size_t)D * ch));
     for (int64_t c0 = 0; c0 < sh.n; c0 += ch) {
       const int64_t cn = std::min(ch, sh.n - c0);
-      GP_LAUNCH(masked_restore_kernel, (unsigned)ceil_div(cn, 256), 256, 0, sh.st, sh.par, sh.Ez + c0 * M, fm, stage, ch, cn);
+      GP_LAUNCH(masked_restore_kernel, (unsigned)ceil_div(cn, 256), 256, 0, sh.st, sh.par, sh.EA + c0 * s->EAS + s->NV, s->EAS, fm, stage,
+                ch, cn);
       double* dst = restored + (sh.n0 - first) + c0;
       cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * ld, stage, sizeof(double) * ch, sizeof(double) * cn, D,
                                         cudaMemcpyDeviceToHost, sh.st);

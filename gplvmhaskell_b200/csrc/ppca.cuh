@@ -52,7 +52,9 @@ struct ShardState {
   int64_t ldx = 0;
   double* X = nullptr;         // n x ldx, observation-major; NaN = missing
   double* Ez = nullptr;        // n x MP (dense generic path / masked path)
-  double* Av = nullptr;        // masked: n x NV  (vech of A_i = ez ez^T + sigma2 Minv_i)
+  double* EA = nullptr;        // masked: n x EAS, row i = [vech(A_i) (NV) | ez_i (M)], A_i = ez ez^T + sigma2 Minv_i
+  double* yy = nullptr;        // masked fused path: |(y_i - mu)_observed|^2 per observation
+  uint32_t* mbits = nullptr;   // masked: n x WPR words, bit d set = feature d of the observation is missing
   double* parblock = nullptr;  // parameter block
   double* stats = nullptr;     // packed statistics (all-reduced), `S` doubles
   double* partials = nullptr;  // nparts x S
@@ -68,6 +70,7 @@ struct ShardState {
 struct gplvm_ppca_session {
   int64_t D = 0, N = 0, M = 0;
   int MP = 0, NV = 0;
+  int EAS = 0, WPR = 0;    // masked: row stride of EA (NV + M), mask words per observation
   bool missing = false;
   bool has_data = false, initialised = false;
   bool centred = false;    // dense: the resident observations have had their feature means subtracted (PPCA.hs:61)
@@ -88,6 +91,9 @@ bool dense_dmma_eligible(const gplvm_ppca_session* s);
 int dense_dmma_prepare(gplvm_ppca_session* s);
 int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int dense_dmma_release(gplvm_ppca_session* s);
+int masked_dmma_b(gplvm_ppca_session* s, ShardState& sh, const double* W, const double* mu, double* bout, double* yyout);
+int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out);
+int masked_dmma_s2(gplvm_ppca_session* s, ShardState& sh, const double* ez, int64_t ldez, double* dst);
 int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
 // masked.cu
 int masked_init_constants(gplvm_ppca_session* s);
@@ -96,12 +102,13 @@ int masked_loglik(gplvm_ppca_session* s, double* ll);
 int masked_restore(gplvm_ppca_session* s, double* restored, int64_t ld);
 // session.cu
 int session_allreduce_stats(gplvm_ppca_session* s, size_t count);
-int launch_reduce_partials(ShardState& sh, int64_t S, int nparts);
+int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst = nullptr);
 
 // Generic split-K statistics GEMM shared by dense.cu and masked.cu (defined in dense.cu).
 // out block 1: rows [0,R1) x Q1 columns, block 2: rows [R1,R) x Q2 columns (Q2 <= Q1).
-enum RowKind { ROWS_DENSE = 0, ROWS_MASKED = 1 };
+// The partial results go through sh.partials (stride Sout per split) and are summed in fixed order into dst.
+enum RowKind { ROWS_DENSE = 0, ROWS_MASKED_VALUES = 1 };
 int launch_stats_gemm(ShardState& sh, RowKind kind, int D, int R1, int R, int Q1, int Q2, const double* Cmat,
-                      int ldc, int Cw1, const double* Cmat2, int ldc2, int64_t S);
+                      int ldc, int Cw1, const double* Cmat2, int ldc2, int64_t Sout, double* dst);
 
 }  // namespace gplvm

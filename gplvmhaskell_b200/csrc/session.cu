@@ -86,7 +86,7 @@ int64_t chunk_obs(int64_t D) {
 
 void free_shard(ShardState& sh) {
   cudaSetDevice(sh.dev);
-  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.Av); cudaFree(sh.parblock); cudaFree(sh.stats);
+  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
   cudaFree(sh.partials); cudaFree(sh.scratch);
   if (sh.tmap) free(sh.tmap);
   if (sh.ev0) cudaEventDestroy(sh.ev0);
@@ -147,8 +147,10 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
   s->MP = s->missing ? (int)M : (s->use_dmma ? 16 : (int)round_up(M, 8));
   if (s->MP > GPLVM_MAX_M) s->MP = GPLVM_MAX_M;
   s->NV = s->MP * (s->MP + 1) / 2;
-  if (s->missing)  // S1 | G  (D x (M+NV)) ; S2 (D x M) ; sum ez (M)
-    s->S = D * (s->MP + s->NV) + (D + 1) * s->MP;
+  s->EAS = s->NV + s->MP;
+  s->WPR = (int)ceil_div(D, 32);
+  if (s->missing)  // complement sums [G^miss | S1^miss] (D x EAS) ; totals (EAS) ; S2 (D x M)
+    s->S = (D + 1) * (int64_t)s->EAS + D * s->MP;
   else             // XEz (D x MP) | EE (MP x MP)
     s->S = (D + s->MP) * s->MP;
   const int nsh = (int)c.shards.size();
@@ -176,8 +178,10 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
     if (s->use_dmma) sh.nparts = std::max(sh.nparts, dense_dmma_nparts(s, sh));
     const size_t parlen = (size_t)D * MP * 3 + (size_t)MP * MP + MP + (size_t)D * 4 + S_COUNT + 64;
     if (e == cudaSuccess) e = cudaMalloc(&sh.X, sizeof(double) * (size_t)sh.n * sh.ldx);
-    if (e == cudaSuccess && (s->missing || !s->use_dmma)) e = cudaMalloc(&sh.Ez, sizeof(double) * (size_t)sh.n * MP);
-    if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.Av, sizeof(double) * (size_t)sh.n * s->NV);
+    if (e == cudaSuccess && (s->missing == s->use_dmma)) e = cudaMalloc(&sh.Ez, sizeof(double) * (size_t)sh.n * MP);  // generic dense Ez / fused masked b
+    if (e == cudaSuccess && s->missing && s->use_dmma) e = cudaMalloc(&sh.yy, sizeof(double) * (size_t)sh.n);
+    if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.EA, sizeof(double) * (size_t)sh.n * s->EAS);
+    if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.mbits, sizeof(uint32_t) * (size_t)sh.n * s->WPR);
     if (e == cudaSuccess) e = cudaMalloc(&sh.parblock, sizeof(double) * parlen);
     if (e == cudaSuccess) e = cudaMemset(sh.parblock, 0, sizeof(double) * parlen);
     if (e == cudaSuccess) e = cudaMalloc(&sh.stats, sizeof(double) * (size_t)std::max<int64_t>(s->S, 3 * D));
