@@ -14,6 +14,7 @@
 //   s2'   = sum_d (syy_d - 2 mu'_d sy_d + mu'_d^2 n_d - 2 w'_d . r_d + w'_d^T G_d w'_d) / #known   (PPCA.hs:140-147)
 // LL (PPCA.hs:149-159) and restore (PPCA.hs:161-168) are separate final passes.
 #include "ppca.cuh"
+#include "tma.cuh"
 
 namespace gplvm {
 int moments_pass(gplvm_ppca_session* s, int mode);
@@ -182,20 +183,55 @@ __global__ void __launch_bounds__(256) masked_bits_kernel(const double* __restri
 
 // Complement sums.  grid = (row blocks, feature groups); 8 warps per CTA; warp w of feature group fg owns the FPW
 // features f0 = (8 fg + w) FPW ... and keeps miss_d[e] for them in REGISTERS: lane l owns e = l + 32 k, k < KPL.
-// For every observation the warp loads its slice of [vech A_i | ez_i] once and adds it to the accumulators of the
-// features that observation misses (warp-uniform tests on the packed mask bits) -- work ~ #missing, fixed order
-// (rows ascending) => deterministic, no atomics.  Warp 0 of feature group 0 also accumulates the totals.
+// Tiles of TR observations ([vech A_i | ez_i] rows are contiguous in HBM, so a tile is ONE 1-D bulk TMA copy, and
+// so is its block of mask words) are staged in shared memory through a 3-deep mbarrier pipeline; every warp reads
+// each observation's slice once and adds it to the accumulators of the features that observation misses
+// (warp-uniform tests on the packed mask bits) -- work ~ #missing, fixed order (rows ascending) => deterministic,
+// no atomics.  Warp 0 of feature group 0 also accumulates the totals.
 // partials: [row block][(D + 1) x eas]  (row D = totals)
+constexpr int MS_STAGES = 3;
+
+// acc[f][:] += a[:] for every feature f whose bit is set in m.  Written as a set-bit loop around a switch so that
+// the compiler keeps REAL (warp-uniform) branches: an if-converted version executes all FPW x KPL additions per
+// observation (dense work); this one executes ~ #missing x KPL.
 template <int KPL, int FPW>
-__global__ void __launch_bounds__(256) masked_miss_sums_kernel(const double* __restrict__ EA, int eas, const uint32_t* __restrict__ mbits,
+__device__ __forceinline__ void add_missing(double (&acc)[FPW][KPL], const double (&a)[KPL], unsigned m) {
+#define GP_ADD_CASE(F)                                   \
+  case F:                                                \
+    if (F < FPW) {                                       \
+      _Pragma("unroll") for (int k = 0; k < KPL; ++k) acc[F < FPW ? F : 0][k] += a[k]; \
+    }                                                    \
+    break;
+  while (m) {
+    const int f = __ffs(m) - 1;
+    m &= m - 1;
+    switch (f) {
+      GP_ADD_CASE(0) GP_ADD_CASE(1) GP_ADD_CASE(2) GP_ADD_CASE(3) GP_ADD_CASE(4) GP_ADD_CASE(5) GP_ADD_CASE(6) GP_ADD_CASE(7)
+      GP_ADD_CASE(8) GP_ADD_CASE(9) GP_ADD_CASE(10) GP_ADD_CASE(11) GP_ADD_CASE(12) GP_ADD_CASE(13) GP_ADD_CASE(14)
+      GP_ADD_CASE(15)
+      default: break;
+    }
+  }
+#undef GP_ADD_CASE
+}
+
+
+template <int KPL, int FPW, int MS_TR, int MINB>
+__global__ void __launch_bounds__(256, MINB) masked_miss_sums_kernel(const double* __restrict__ EA, int eas, const uint32_t* __restrict__ mbits,
                                                                int wpr, int64_t n_obs, int64_t rows_per_cta, int D,
                                                                double* __restrict__ partials, int64_t Spart,
                                                                const double* __restrict__ scal) {
   if (scal[S_DONE] != 0.0) return;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  extern __shared__ __align__(128) uint8_t ms_smem[];
+  const int ea_bytes = (MS_TR * eas * 8 + 15) & ~15;
+  const int mk_bytes = (MS_TR * wpr * 4 + 15) & ~15;
+  const int stage_bytes = ea_bytes + mk_bytes;
+  const uint32_t sm_u = smem_u32(ms_smem);
+  const uint32_t bar_u = sm_u + MS_STAGES * stage_bytes;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int f0 = ((int)blockIdx.y * 8 + w) * FPW;
   const bool totals = (blockIdx.y == 0 && w == 0);
-  if (f0 >= D && !totals) return;
+  const bool has_feat = f0 < D;
   double acc[FPW][KPL], tot[KPL];
 #pragma unroll
   for (int f = 0; f < FPW; ++f)
@@ -205,56 +241,75 @@ __global__ void __launch_bounds__(256) masked_miss_sums_kernel(const double* __r
   for (int k = 0; k < KPL; ++k) tot[k] = 0.0;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(n_obs, r0 + rows_per_cta);
+  const int64_t ntiles = (r1 > r0) ? (r1 - r0 + MS_TR - 1) / MS_TR : 0;
   const int word = f0 >> 5, shift = f0 & 31;
   const unsigned fmask = (FPW >= 32) ? 0xffffffffu : ((1u << FPW) - 1u);
-  const bool has_feat = f0 < D;
-  int64_t r = r0;
-  for (; r + 1 < r1; r += 2) {  // two observations in flight
-    double a0[KPL], a1[KPL];
-#pragma unroll
-    for (int k = 0; k < KPL; ++k) {
-      const int e = lane + 32 * k;
-      a0[k] = (e < eas) ? EA[r * eas + e] : 0.0;
-      a1[k] = (e < eas) ? EA[(r + 1) * eas + e] : 0.0;
-    }
-    const unsigned m0 = has_feat ? ((mbits[r * wpr + word] >> shift) & fmask) : 0u;
-    const unsigned m1 = has_feat ? ((mbits[(r + 1) * wpr + word] >> shift) & fmask) : 0u;
-    if (totals) {
-#pragma unroll
-      for (int k = 0; k < KPL; ++k) tot[k] += a0[k];
-#pragma unroll
-      for (int k = 0; k < KPL; ++k) tot[k] += a1[k];
-    }
-#pragma unroll
-    for (int f = 0; f < FPW; ++f) {
-      if (m0 & (1u << f)) {
-#pragma unroll
-        for (int k = 0; k < KPL; ++k) acc[f][k] += a0[k];
-      }
-      if (m1 & (1u << f)) {
-#pragma unroll
-        for (int k = 0; k < KPL; ++k) acc[f][k] += a1[k];
-      }
-    }
+
+  if (tid == 0) {
+    for (int s = 0; s < MS_STAGES; ++s) mbar_init(bar_u + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (; r < r1; ++r) {
-    double a0[KPL];
+  __syncthreads();
+  auto issue = [&](int64_t i) {  // thread 0: stage i % STAGES <- tile i (mask block copied whole: mbits is padded by MS_TR rows)
+    const int s = (int)(i % MS_STAGES);
+    const int64_t ra = r0 + i * MS_TR;
+    const int rows = (int)min((int64_t)MS_TR, r1 - ra);
+    const uint32_t dst = sm_u + s * stage_bytes;
+    const uint32_t eb = (uint32_t)((rows * eas * 8 + 15) & ~15);  // EA is padded: the rounded-up tail stays inside it
+    mbar_expect_tx(bar_u + 8 * s, eb + (uint32_t)mk_bytes);
+    bulk_load_1d(dst, EA + ra * eas, eb, bar_u + 8 * s);
+    bulk_load_1d(dst + ea_bytes, mbits + ra * wpr, (uint32_t)mk_bytes, bar_u + 8 * s);
+  };
+  if (tid == 0)
+    for (int64_t i = 0; i < MS_STAGES && i < ntiles; ++i) issue(i);
+
+  for (int64_t i = 0; i < ntiles; ++i) {
+    const int s = (int)(i % MS_STAGES);
+    const int rows = (int)min((int64_t)MS_TR, r1 - (r0 + i * MS_TR));
+    mbar_wait(bar_u + 8 * s, (uint32_t)((i / MS_STAGES) & 1));
+    const double* tile = reinterpret_cast<const double*>(ms_smem + s * stage_bytes);
+    const uint32_t* mk = reinterpret_cast<const uint32_t*>(ms_smem + s * stage_bytes + ea_bytes);
+    if (has_feat || totals) {
+      int r = 0;
+      for (; r + 1 < rows; r += 2) {  // two observations in flight
+        double a0[KPL], a1[KPL];
 #pragma unroll
-    for (int k = 0; k < KPL; ++k) {
-      const int e = lane + 32 * k;
-      a0[k] = (e < eas) ? EA[r * eas + e] : 0.0;
-    }
-    const unsigned m0 = has_feat ? ((mbits[r * wpr + word] >> shift) & fmask) : 0u;
-    if (totals) {
+        for (int k = 0; k < KPL; ++k) {
+          const int e = lane + 32 * k;
+          a0[k] = (e < eas) ? tile[r * eas + e] : 0.0;
+          a1[k] = (e < eas) ? tile[(r + 1) * eas + e] : 0.0;
+        }
+        const unsigned m0 = has_feat ? ((mk[r * wpr + word] >> shift) & fmask) : 0u;
+        const unsigned m1 = has_feat ? ((mk[(r + 1) * wpr + word] >> shift) & fmask) : 0u;
+        if (totals) {
 #pragma unroll
-      for (int k = 0; k < KPL; ++k) tot[k] += a0[k];
-    }
+          for (int k = 0; k < KPL; ++k) tot[k] += a0[k];
 #pragma unroll
-    for (int f = 0; f < FPW; ++f)
-      if (m0 & (1u << f)) {
-#pragma unroll
-        for (int k = 0; k < KPL; ++k) acc[f][k] += a0[k];
+          for (int k = 0; k < KPL; ++k) tot[k] += a1[k];
+        }
+        add_missing<KPL, FPW>(acc, a0, m0);
+        add_missing<KPL, FPW>(acc, a1, m1);
       }
+      if (r < rows) {
+        double a0[KPL];
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+          const int e = lane + 32 * k;
+          a0[k] = (e < eas) ? tile[r * eas + e] : 0.0;
+        }
+        const unsigned m0 = has_feat ? ((mk[r * wpr + word] >> shift) & fmask) : 0u;
+        if (totals) {
+#pragma unroll
+          for (int k = 0; k < KPL; ++k) tot[k] += a0[k];
+        }
+        add_missing<KPL, FPW>(acc, a0, m0);
+      }
+    }
+    __syncthreads();  // every warp is done with this stage
+    if (tid == 0 && i + MS_STAGES < ntiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(i + MS_STAGES);
+    }
   }
   double* out = partials + (int64_t)blockIdx.x * Spart;
   if (has_feat) {
@@ -535,19 +590,32 @@ int masked_init_constants(gplvm_ppca_session* s) {
 static int launch_miss_sums(gplvm_ppca_session* s, ShardState& sh) {
   const int D = (int)s->D, eas = s->EAS;
   const int64_t Spart = (int64_t)(D + 1) * eas;
-  const bool small = eas <= 160;   // M <= 16: 5 values per lane, 16 features per warp; else 18 per lane, 2 features
-  const int fpw = small ? 16 : 2;
+  const bool small = eas <= 160;   // M <= 16: 5 values per lane, 8 features per warp; else 18 per lane, 2 features
+  const int fpw = small ? 8 : 2;
+  const int tr = small ? 16 : 8;   // observations per pipeline stage
   const int fgroups = (int)ceil_div(D, 8 * fpw);
-  int rb = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * 148) / fgroups), sh.nparts);
-  const int64_t rows_per_cta = std::max<int64_t>(ceil_div(sh.n, rb), 2);
+  int rb = (int)std::min<int64_t>(std::max<int64_t>(1, (small ? 2 : 1) * sm_count(sh.dev) / fgroups), sh.nparts);
+  const int64_t rows_per_cta = round_up(std::max<int64_t>(ceil_div(sh.n, rb), 4), 4);  // 16-byte aligned tile starts
   rb = (int)ceil_div(sh.n, rows_per_cta);
+  const int smem = MS_STAGES * (((tr * eas * 8 + 15) & ~15) + ((tr * s->WPR * 4 + 15) & ~15)) + 64;
+  static bool attr_done = false;
+  if (!attr_done) {
+    for (ShardState& t : s->sh) {
+      CUDA_TRY(cudaSetDevice(t.dev));
+      CUDA_TRY(cudaFuncSetAttribute((masked_miss_sums_kernel<5, 8, 16, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute((masked_miss_sums_kernel<18, 2, 8, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    attr_done = true;
+  }
+  if (smem > 200 * 1024) return fail(GPLVM_ERR_ARG, "missing-data PPCA: M too large for the statistics kernel");
   dim3 grid(rb, fgroups);
   if (small)
-    GP_LAUNCH((masked_miss_sums_kernel<5, 16>), grid, 256, 0, sh.st, sh.EA, eas, sh.mbits, s->WPR, sh.n, rows_per_cta, D, sh.partials,
-              Spart, sh.par.scal);
+    GP_LAUNCH((masked_miss_sums_kernel<5, 8, 16, 2>), grid, 256, smem, sh.st, sh.EA, eas, sh.mbits, s->WPR, sh.n, rows_per_cta, D,
+              sh.partials, Spart, sh.par.scal);
   else
-    GP_LAUNCH((masked_miss_sums_kernel<18, 2>), grid, 256, 0, sh.st, sh.EA, eas, sh.mbits, s->WPR, sh.n, rows_per_cta, D, sh.partials,
-              Spart, sh.par.scal);
+    GP_LAUNCH((masked_miss_sums_kernel<18, 2, 8, 1>), grid, 256, smem, sh.st, sh.EA, eas, sh.mbits, s->WPR, sh.n, rows_per_cta, D,
+              sh.partials, Spart, sh.par.scal);
   return launch_reduce_partials(sh, Spart, rb, sh.stats);
 }
 
@@ -562,7 +630,8 @@ int masked_enqueue_step(gplvm_ppca_session* s) {
       // fused path (M = 16): b_i by TMA + DMMA, per-observation register solver, sparse complement sums, S2 by DMMA
       GP_TRY(masked_dmma_b(s, sh, sh.par.W, sh.par.mu, sh.Ez, sh.yy));
       GP_TRY(masked_fused_solve(s, sh, sh.Ez, sh.yy, false, nullptr));
-      GP_TRY(launch_miss_sums(s, sh));
+      if (D >= 128) GP_TRY(masked_fused_miss_sums(s, sh, sh.stats));
+      else GP_TRY(launch_miss_sums(s, sh));
       GP_TRY(masked_dmma_s2(s, sh, sh.EA + s->NV, s->EAS, s2dst));
     } else {
       const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(sh.n, EW), 148 * 8);

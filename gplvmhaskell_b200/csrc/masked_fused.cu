@@ -9,10 +9,10 @@
 // registers.
 //   build    : M_i = C0 - sum_{d missing} w_d w_d^T  (complement form: work ~ #missing); the missing features come
 //              from the packed mask bits, w_d from shared memory (W is D x 16, 32 KB at D = 256).
-//   factor   : right-looking Cholesky on the full symmetric column set (lane c reads L[c][k] = M[k][c]/L[k][k] from
-//              its OWN registers by symmetry; only the pivot and column k travel by __shfl_sync); reciprocal
-//              square roots by rsqrt.approx.f64 + 2 Newton steps.
-//   invert   : T = L^-1 by forward substitution (column c in lane c), M_i^-1 = T^T T, ez = M_i^-1 b.
+//   invert   : 16 symmetric sweeps (Gauss-Jordan on the SPD matrix, pivots = Schur complements > 0) turn the
+//              registers into -M_i^-1; lane c reads M[k][c] from its OWN column by symmetry, only column k travels
+//              by __shfl_sync; reciprocals by rcp.approx.f64 + 2 Newton steps; log det M_i = sum log pivots.
+//   outputs  : ez = M_i^-1 b, A_i = ez ez^T + sigma^2 M_i^-1.
 // b_i (and |y_c|^2 for the likelihood) come from the TMA + DMMA pass in dense_dmma.cu (MODE_MASKED_B).
 #include "ppca.cuh"
 #include "tma.cuh"
@@ -24,13 +24,14 @@ constexpr int MF = 16;
 constexpr int NVF = MF * (MF + 1) / 2;   // 136
 constexpr int EASF = NVF + MF;           // 152
 
-__device__ __forceinline__ double rsqrt_nr(double x) {
+// 1 / x for a positive normal x: hardware seed + 2 Newton steps (relative error ~ 1 ulp)
+__device__ __forceinline__ double rcp_nr(double x) {
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
-    const double e = fma(-x * y, y, 1.0);
-    y = fma(0.5 * y, e, y);
+    const double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
   }
   return y;
 }
@@ -53,15 +54,20 @@ __global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __re
   const double s2 = p.scal[S_SIGMA2];
   const int lane = threadIdx.x & 31, c = lane & 15;
   constexpr unsigned hmask = 0xffffffffu;  // both half-warps run every shuffle together (width 16 keeps them apart)
-  const int64_t pair0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;  // warp-uniform
-  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * 2;
+  // The trip count depends on blockIdx only, so the compiler can see that every warp stays converged around the
+  // shuffles (a warp whose pair lies past the end recomputes the last observation and stores nothing).
+  const int64_t cta0 = (int64_t)blockIdx.x * 16;            // 8 warps x 2 observations per CTA and iteration
+  const int64_t stride = (int64_t)gridDim.x * 16;
+  const int64_t iters = (n_obs > cta0) ? (n_obs - cta0 + stride - 1) / stride : 0;
+  const int wpair = (threadIdx.x >> 5) * 2;
   const uint32_t ws_u = smem_u32(Ws);
   double llacc = 0.0;
   const double log2pi = 1.8378770664093453, logs2 = LL ? log(s2) : 0.0;
 
-  for (int64_t nb = pair0; nb < n_obs; nb += stride) {
-    const bool valid = nb + (lane >> 4) < n_obs;              // an odd tail leaves the upper half-warp idle:
-    const int64_t n = valid ? nb + (lane >> 4) : n_obs - 1;   // it recomputes the last observation and stores nothing
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t nb = cta0 + it * stride + wpair;
+    const bool valid = nb + (lane >> 4) < n_obs;
+    const int64_t n = valid ? nb + (lane >> 4) : n_obs - 1;
     // ---- build M_i -----------------------------------------------------------------------------------------
     double m[MF];
 #pragma unroll
@@ -73,68 +79,51 @@ __global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __re
     for (int wd = 0; wd < WPRT; ++wd) {
       uint32_t bits = __shfl_sync(hmask, mw, wd, 16);
       nmiss += __popc(bits);
-      while (bits) {
-        const int j = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const uint32_t wr = ws_u + (uint32_t)((wd * 32 + j) * (MF * 8));
-        double wv[MF];
+      // warp-uniform trip count (both half-warps stay converged for the shuffles that follow)
+      while (__any_sync(hmask, bits != 0u)) {
+        if (bits) {
+          const int j = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const uint32_t wr = ws_u + (uint32_t)((wd * 32 + j) * (MF * 8));
+          double wv[MF];
 #pragma unroll
-        for (int q = 0; q < MF / 2; ++q) lds128(wr + q * 16, wv[2 * q], wv[2 * q + 1]);
-        const double wc = lds64(wr + c * 8);
+          for (int q = 0; q < MF / 2; ++q) lds128(wr + q * 16, wv[2 * q], wv[2 * q + 1]);
+          const double wc = lds64(wr + c * 8);
 #pragma unroll
-        for (int a = 0; a < MF; ++a) m[a] = fma(-wv[a], wc, m[a]);
+          for (int a = 0; a < MF; ++a) m[a] = fma(-wv[a], wc, m[a]);
+        }
       }
-      __syncwarp();
     }
     // every feature missing: unsupported by the reference (Util.hs:81); flagged, outputs zeroed below
     const bool empty = nmiss >= DD;
     if (empty && c == 0) set_err(p.scal, 2.0);
-    // ---- Cholesky: lc[a] = L[a][c] (a > c), lc[c] = 1 / L[c][c] -------------------------------------------
-    double lc[MF];
+    // ---- in-place inverse by symmetric sweeps: after sweeping k = 0..15 the matrix is -M_i^-1 ------------------
+    // Step k (pivot p = M[k][k], d = 1/p):  B[i][j] = M[i][j] - M[i][k] M[k][j] d,  B[i][k] = M[i][k] d,  B[k][k] = -d.
+    // Lane c reads M[k][c] from its own column by symmetry; only column k travels (shuffles from lane k).  Lane k's
+    // own column is kept UNSCALED with the factor d remembered in `scale` (applied once at the end), which keeps the
+    // update formula identical in every lane (r = 0 makes it a no-op in lane k) -- no per-entry selects.
     bool ok = true;
-    double yprod = 1.0;
+    double pprod = 1.0, scale = 1.0;
 #pragma unroll
     for (int k = 0; k < MF; ++k) {
       const double pk = __shfl_sync(hmask, m[k], k, 16);
       ok = ok && (pk > 0.0);
-      const double y = rsqrt_nr(pk);
-      if (LL) yprod *= y;
-      const double lck = m[k] * y;
-      if (c == k) lc[k] = y;
+      if (LL) pprod *= pk;
+      const double d = rcp_nr(pk);
+      const double r = (c == k) ? 0.0 : m[k] * d;
 #pragma unroll
-      for (int a = k + 1; a < MF; ++a) {
-        const double sa = m[a] * y;
-        if (c == k) lc[a] = sa;
-        const double lak = __shfl_sync(hmask, sa, k, 16);
-        m[a] = fma(-lak, lck, m[a]);
+      for (int a = 0; a < MF; ++a) {
+        if (a == k) continue;
+        const double ca = __shfl_sync(hmask, m[a], k, 16);
+        m[a] = fma(-ca, r, m[a]);
       }
+      m[k] = (c == k) ? -1.0 : r;
+      if (c == k) scale = d;
     }
     if (!ok && c == 0) set_err(p.scal, 1.0);
-    // ---- T = L^-1 (column c in lane c) ---------------------------------------------------------------------
-    double tt[MF];
+    double mi[MF];   // column c of M_i^-1
 #pragma unroll
-    for (int i = 0; i < MF; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < i; ++k) {
-        const double lik = __shfl_sync(hmask, lc[i], k, 16);
-        s = fma(lik, tt[k], s);
-      }
-      const double di = __shfl_sync(hmask, lc[i], i, 16);
-      tt[i] = (i == c) ? di : -s * di;
-    }
-    // ---- M_i^-1 = T^T T (column c), ez = M_i^-1 b -----------------------------------------------------------
-    double mi[MF];
-#pragma unroll
-    for (int a = 0; a < MF; ++a) {
-      double s = 0.0;
-#pragma unroll
-      for (int i = a; i < MF; ++i) {
-        const double tia = __shfl_sync(hmask, tt[i], a, 16);
-        s = fma(tia, tt[i], s);
-      }
-      mi[a] = s;
-    }
+    for (int a = 0; a < MF; ++a) mi[a] = -scale * m[a];
     double ez = 0.0;
 #pragma unroll
     for (int a = 0; a < MF; ++a) ez = fma(mi[a], __shfl_sync(hmask, bc, a, 16), ez);
@@ -154,7 +143,7 @@ __global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __re
       for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(hmask, dot, o, 16);
       if (c == 0 && valid && !empty) {
         const double cnt = (double)(DD - nmiss);
-        const double logdetM = -2.0 * log(yprod);
+        const double logdetM = log(pprod);
         llacc += cnt * log2pi + ((cnt - (double)MF) * logs2 + logdetM) + (yy[n] - dot) / s2;
       }
     }
@@ -163,6 +152,132 @@ __global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __re
     const double tsum = block_sum(llacc, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = tsum;
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Complement sums on the FP64 tensor cores:  miss (D x 152) = Miss^T (D x n) . [vech A | ez] (n x 152), where
+// Miss[i][d] = 1.0 when observation i misses feature d.  MMA axes: M = features, N = the 152 statistics, K =
+// observations.  A fragments are decoded from the packed mask bits (exact 0.0 / 1.0), B fragments come straight
+// from the TMA-staged [vech A | ez] tile (row pitch 1216 B => the 4-row x 8-column fragment reads are
+// bank-conflict free).  8 warps x 16 features per CTA; grid = (row blocks, D / 128).  Warp 0 of feature group 0
+// also accumulates the column totals.  Fixed accumulation order => deterministic.
+// partials: [row block][(D + 1) x 152]  (row D = totals)
+constexpr int KB_TR = 32;       // observations per stage
+constexpr int KB_STAGES = 3;
+constexpr int KB_NT = EASF / 8; // 19 n-tiles
+
+template <int DD>
+__global__ void __launch_bounds__(256, 1) masked_miss_dmma_kernel(const double* __restrict__ EA, const uint32_t* __restrict__ mbits,
+                                                                 int64_t n_obs, int64_t rows_per_cta, double* __restrict__ partials,
+                                                                 int64_t Spart, const double* __restrict__ scal) {
+  constexpr int WPRT = DD / 32;
+  constexpr int EA_BYTES = KB_TR * EASF * 8;
+  constexpr int MK_BYTES = KB_TR * WPRT * 4;
+  constexpr int STAGE_BYTES = EA_BYTES + MK_BYTES;
+  if (scal[S_DONE] != 0.0) return;
+  extern __shared__ __align__(128) uint8_t kb_smem[];
+  const uint32_t sm_u = smem_u32(kb_smem);
+  const uint32_t bar_u = sm_u + KB_STAGES * STAGE_BYTES;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int f0 = ((int)blockIdx.y * 8 + w) * 16;     // this warp's 16 features (2 m-tiles)
+  const bool totals = (blockIdx.y == 0 && w == 0);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(n_obs, r0 + rows_per_cta);
+  const int64_t ntiles = (r1 > r0) ? (r1 - r0 + KB_TR - 1) / KB_TR : 0;
+
+  // stale shared memory must not hold NaN patterns: rows past the end of a partial tile are multiplied by 0.0
+  for (int e = tid; e < KB_STAGES * STAGE_BYTES / 8; e += 256) reinterpret_cast<double*>(kb_smem)[e] = 0.0;
+  if (tid == 0) {
+    for (int s = 0; s < KB_STAGES; ++s) mbar_init(bar_u + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  auto issue = [&](int64_t i) {
+    const int s = (int)(i % KB_STAGES);
+    const int64_t ra = r0 + i * KB_TR;
+    const int rows = (int)min((int64_t)KB_TR, r1 - ra);
+    const uint32_t dst = sm_u + s * STAGE_BYTES;
+    mbar_expect_tx(bar_u + 8 * s, (uint32_t)(rows * EASF * 8 + MK_BYTES));
+    bulk_load_1d(dst, EA + ra * EASF, (uint32_t)(rows * EASF * 8), bar_u + 8 * s);
+    bulk_load_1d(dst + EA_BYTES, mbits + ra * WPRT, (uint32_t)MK_BYTES, bar_u + 8 * s);  // mbits is padded by >= KB_TR rows
+  };
+  if (tid == 0)
+    for (int64_t i = 0; i < KB_STAGES && i < ntiles; ++i) issue(i);
+
+  double acc[2][KB_NT][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < KB_NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  double tot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const int word = f0 >> 5, shift = (f0 & 31) + g;   // bit of feature f0 + g ; + 8 for the second m-tile
+
+  for (int64_t i = 0; i < ntiles; ++i) {
+    const int s = (int)(i % KB_STAGES);
+    const int rows = (int)min((int64_t)KB_TR, r1 - (r0 + i * KB_TR));
+    mbar_wait(bar_u + 8 * s, (uint32_t)((i / KB_STAGES) & 1));
+    const uint32_t tile_u = sm_u + s * STAGE_BYTES;
+    const uint32_t* mk = reinterpret_cast<const uint32_t*>(kb_smem + s * STAGE_BYTES + EA_BYTES);
+    if (totals) {
+      const double* tile = reinterpret_cast<const double*>(kb_smem + s * STAGE_BYTES);
+      for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int e = lane + 32 * k;
+          if (e < EASF) tot[k] += tile[r * EASF + e];
+        }
+      }
+    }
+#pragma unroll 2
+    for (int ks = 0; ks < KB_TR / 4; ++ks) {
+      const int r = ks * 4 + t;
+      const uint32_t bits = (r < rows) ? (mk[r * WPRT + word] >> shift) : 0u;
+      const double a0 = (bits & 1u) ? 1.0 : 0.0;
+      const double a1 = (bits & 0x100u) ? 1.0 : 0.0;
+      const uint32_t brow = tile_u + (uint32_t)((r * EASF + g) * 8);
+#pragma unroll
+      for (int nt = 0; nt < KB_NT; ++nt) {
+        const double b = lds64(brow + nt * 64);
+        dmma(acc[0][nt], a0, b);
+        dmma(acc[1][nt], a1, b);
+      }
+    }
+    __syncthreads();  // every warp is done with this stage
+    if (tid == 0 && i + KB_STAGES < ntiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(i + KB_STAGES);
+    }
+  }
+  double* out = partials + (int64_t)blockIdx.x * Spart;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < KB_NT; ++nt)
+      *reinterpret_cast<double2*>(&out[(int64_t)(f0 + mt * 8 + g) * EASF + nt * 8 + 2 * t]) =
+          make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+  if (totals) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int e = lane + 32 * k;
+      if (e < EASF) out[(int64_t)DD * EASF + e] = tot[k];
+    }
+  }
+}
+
+template <int DD>
+int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart) {
+  const int smem = KB_STAGES * (KB_TR * EASF * 8 + KB_TR * (DD / 32) * 4) + 64;
+  static bool attr_done[64] = {};
+  if (!attr_done[sh.dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute((masked_miss_dmma_kernel<DD>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done[sh.dev & 63] = true;
+  }
+  dim3 grid(rb, DD / 128 > 0 ? DD / 128 : 1);
+  GP_LAUNCH((masked_miss_dmma_kernel<DD>), grid, 256, smem, sh.st, sh.EA, sh.mbits, sh.n, rows_per_cta, sh.partials, Spart,
+            sh.par.scal);
+  return GPLVM_OK;
 }
 
 template <int DD, bool LL>
@@ -190,6 +305,24 @@ int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc
     case 256: return ll ? launch_solve<256, true>(sh, bsrc, yy, grid) : launch_solve<256, false>(sh, bsrc, yy, grid);
     default: return fail(GPLVM_ERR_STATE, "fused masked solver: unsupported D");
   }
+}
+
+
+// complement sums [G^miss | S1^miss] (D x 152) + totals (152) into dst (length (D + 1) x 152)
+int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
+  const int64_t Spart = (int64_t)(s->D + 1) * EASF;
+  const int fgroups = (int)std::max<int64_t>(1, s->D / 128);
+  int rb = (int)std::min<int64_t>(std::max<int64_t>(1, sm_count(sh.dev) / fgroups), sh.nparts);
+  const int64_t rows_per_cta = round_up(std::max<int64_t>(ceil_div(sh.n, rb), 4), 4);
+  rb = (int)ceil_div(sh.n, rows_per_cta);
+  int rc;
+  switch (s->D) {
+    case 128: rc = launch_miss_dmma<128>(sh, rb, rows_per_cta, Spart); break;
+    case 256: rc = launch_miss_dmma<256>(sh, rb, rows_per_cta, Spart); break;
+    default: return fail(GPLVM_ERR_STATE, "fused masked statistics: unsupported D");
+  }
+  GP_TRY(rc);
+  return launch_reduce_partials(sh, Spart, rb, dst);
 }
 
 }  // namespace gplvm

@@ -93,6 +93,7 @@ int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int dense_dmma_release(gplvm_ppca_session* s);
 int masked_dmma_b(gplvm_ppca_session* s, ShardState& sh, const double* W, const double* mu, double* bout, double* yyout);
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out);
+int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
 int masked_dmma_s2(gplvm_ppca_session* s, ShardState& sh, const double* ez, int64_t ldez, double* dst);
 int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
 // masked.cu
