@@ -5,10 +5,11 @@
 // Reference: emStepsMissed.stepOne, src/GPLVM/PPCA.hs:106-117 (M_i = sigma^2 I + W_i^T W_i, invMP, expXi) and the
 // per-observation log-likelihood terms of PPCA.hs:149-159 (through the determinant lemma).
 //
-// Mapping: one HALF-WARP per observation, lane c (0..15) owns column c of the symmetric 16 x 16 matrix in 16
-// registers.
-//   build    : M_i = C0 - sum_{d missing} w_d w_d^T  (complement form: work ~ #missing); the missing features come
-//              from the packed mask bits, w_d from shared memory (W is D x 16, 32 KB at D = 256).
+// Mapping: one warp per PAIR of observations.
+//   build    : M_i = C0 - W_miss^T W_miss (complement form: work ~ #missing).  The missing-feature indices are compacted
+//              from the packed mask bits; the Gram matrix is a K-compacted mma.sync.m8n8k4.f64 product whose operands
+//              are gathered rows of W in shared memory (W is D x 16, pitch 18 doubles).
+//   then one HALF-WARP per observation, lane c (0..15) owns column c of the symmetric 16 x 16 matrix in 16 registers:
 //   invert   : 16 symmetric sweeps (Gauss-Jordan on the SPD matrix, pivots = Schur complements > 0) turn the
 //              registers into -M_i^-1; lane c reads M[k][c] from its OWN column by symmetry, only column k travels
 //              by __shfl_sync; reciprocals by rcp.approx.f64 + 2 Newton steps; log det M_i = sum log pivots.
@@ -23,6 +24,7 @@ namespace {
 constexpr int MF = 16;
 constexpr int NVF = MF * (MF + 1) / 2;   // 136
 constexpr int EASF = NVF + MF;           // 152
+constexpr int WP = 18;                   // pitch (doubles) of the W rows in shared memory: spreads gathered rows over the banks
 
 // 1 / x for a positive normal x: hardware seed + 2 Newton steps (relative error ~ 1 ulp)
 __device__ __forceinline__ double rcp_nr(double x) {
@@ -45,12 +47,21 @@ __global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __re
   constexpr int WPRT = DD / 32;
   if (!LL && p.scal[S_DONE] != 0.0) return;
   extern __shared__ double sm[];
-  double* Ws = sm;                 // DD x 16
-  double* C0s = sm + DD * MF;      // 16 x 16 : s2 I + W^T W  (kept in p.Minv by the masked prep kernel)
+  double* Ws = sm;                               // (DD + 1) x WP : rows of W, pitch 18 doubles; row DD = 0 (list padding)
+  double* C0s = Ws + (DD + 1) * WP;              // 16 x 16 : s2 I + W^T W  (kept in p.Minv by the masked prep kernel)
+  double* Msm = C0s + MF * MF;                   // per warp: 2 x 16 x 17 staging of the two W_miss^T W_miss matrices
+  uint16_t* lists = reinterpret_cast<uint16_t*>(Msm + 8 * 2 * MF * 17);  // per warp: 2 x DD missing-feature indices
   __shared__ double red[40];
-  for (int e = threadIdx.x; e < DD * MF; e += blockDim.x) Ws[e] = p.W[e];
+  for (int e = threadIdx.x; e < (DD + 1) * MF; e += blockDim.x) {
+    const int d = e >> 4, a = e & 15;
+    Ws[d * WP + a] = (d < DD) ? p.W[e] : 0.0;
+  }
   for (int e = threadIdx.x; e < MF * MF; e += blockDim.x) C0s[e] = p.Minv[e];
   __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  double* Mw = Msm + warp * (2 * MF * 17);
+  uint16_t* lst = lists + warp * (2 * DD);
+  const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
   const double s2 = p.scal[S_SIGMA2];
   const int lane = threadIdx.x & 31, c = lane & 15;
   constexpr unsigned hmask = 0xffffffffu;  // both half-warps run every shuffle together (width 16 keeps them apart)
@@ -60,7 +71,6 @@ __global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __re
   const int64_t stride = (int64_t)gridDim.x * 16;
   const int64_t iters = (n_obs > cta0) ? (n_obs - cta0 + stride - 1) / stride : 0;
   const int wpair = (threadIdx.x >> 5) * 2;
-  const uint32_t ws_u = smem_u32(Ws);
   double llacc = 0.0;
   const double log2pi = 1.8378770664093453, logs2 = LL ? log(s2) : 0.0;
 
@@ -68,32 +78,63 @@ __global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __re
     const int64_t nb = cta0 + it * stride + wpair;
     const bool valid = nb + (lane >> 4) < n_obs;
     const int64_t n = valid ? nb + (lane >> 4) : n_obs - 1;
-    // ---- build M_i -----------------------------------------------------------------------------------------
-    double m[MF];
-#pragma unroll
-    for (int a = 0; a < MF; ++a) m[a] = C0s[a * MF + c];
+    // ---- build M_i = C0 - W_miss^T W_miss on the tensor cores -------------------------------------------------
+    // (a) compact the missing-feature indices of the warp's two observations (ballot-free: every lane tests its own
+    //     bit of each mask word and ranks itself with a popcount); (b) K-compacted Gram matrices: k runs over the
+    //     MISSING features only, 4 per mma.sync.m8n8k4, gathered rows of W as both operands (3 tiles: 00, 01, 11);
+    //     (c) through shared memory into the column-per-lane layout of the sweeps.
     const uint32_t mw = (c < WPRT) ? mbits[n * WPRT + c] : 0u;
     const double bc = bsrc[n * MF + c];
-    int nmiss = 0;
+    int cnt0 = 0, cnt1 = 0;
 #pragma unroll
     for (int wd = 0; wd < WPRT; ++wd) {
-      uint32_t bits = __shfl_sync(hmask, mw, wd, 16);
-      nmiss += __popc(bits);
-      // warp-uniform trip count (both half-warps stay converged for the shuffles that follow)
-      while (__any_sync(hmask, bits != 0u)) {
-        if (bits) {
-          const int j = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const uint32_t wr = ws_u + (uint32_t)((wd * 32 + j) * (MF * 8));
-          double wv[MF];
+      const uint32_t b0 = __shfl_sync(hmask, mw, wd);
+      const uint32_t b1 = __shfl_sync(hmask, mw, 16 + wd);
+      const uint32_t lt = (1u << lane) - 1u;
+      if ((b0 >> lane) & 1u) lst[cnt0 + __popc(b0 & lt)] = (uint16_t)(wd * 32 + lane);
+      if ((b1 >> lane) & 1u) lst[DD + cnt1 + __popc(b1 & lt)] = (uint16_t)(wd * 32 + lane);
+      cnt0 += __popc(b0);
+      cnt1 += __popc(b1);
+    }
+    const int nmiss = (lane & 16) ? cnt1 : cnt0;
+    const int nks = (max(cnt0, cnt1) + 3) >> 2;
+    for (int e = lane; e < nks * 4; e += 32) {  // pad with the zero row of Ws
+      if (e >= cnt0) lst[e] = (uint16_t)DD;
+      if (e >= cnt1) lst[DD + e] = (uint16_t)DD;
+    }
+    __syncwarp();
+    double g00[2][2], g01[2][2], g11[2][2];
 #pragma unroll
-          for (int q = 0; q < MF / 2; ++q) lds128(wr + q * 16, wv[2 * q], wv[2 * q + 1]);
-          const double wc = lds64(wr + c * 8);
+    for (int h = 0; h < 2; ++h) g00[h][0] = g00[h][1] = g01[h][0] = g01[h][1] = g11[h][0] = g11[h][1] = 0.0;
+    for (int ks = 0; ks < nks; ++ks) {
 #pragma unroll
-          for (int a = 0; a < MF; ++a) m[a] = fma(-wv[a], wc, m[a]);
-        }
+      for (int h = 0; h < 2; ++h) {
+        const int d = lst[h * DD + ks * 4 + t];
+        const double f0 = Ws[d * WP + g], f1 = Ws[d * WP + 8 + g];
+        dmma(g00[h], f0, f0);
+        dmma(g01[h], f0, f1);
+        dmma(g11[h], f1, f1);
       }
     }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double* Mh = Mw + h * (MF * 17);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        Mh[g * 17 + 2 * t + q] = g00[h][q];
+        Mh[g * 17 + 8 + 2 * t + q] = g01[h][q];
+        Mh[(8 + 2 * t + q) * 17 + g] = g01[h][q];
+        Mh[(8 + g) * 17 + 8 + 2 * t + q] = g11[h][q];
+      }
+    }
+    __syncwarp();
+    double m[MF];
+    {
+      const double* Mh = Mw + (lane >> 4) * (MF * 17);
+#pragma unroll
+      for (int a = 0; a < MF; ++a) m[a] = C0s[a * MF + c] - Mh[a * 17 + c];
+    }
+    __syncwarp();
     // every feature missing: unsupported by the reference (Util.hs:81); flagged, outputs zeroed below
     const bool empty = nmiss >= DD;
     if (empty && c == 0) set_err(p.scal, 2.0);
@@ -282,7 +323,7 @@ int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart
 
 template <int DD, bool LL>
 int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid) {
-  const int smem = (DD * MF + MF * MF) * (int)sizeof(double);
+  const int smem = ((DD + 1) * WP + MF * MF + 8 * 2 * MF * 17) * (int)sizeof(double) + 8 * 2 * DD * (int)sizeof(uint16_t);
   static bool attr_done[64] = {};
   if (!attr_done[sh.dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute((masked_solve_kernel<DD, LL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
