@@ -258,7 +258,8 @@ def main():
     ach_tf = flop_obs * count / (k_ms * 1e-3) * 1e-12
     ach_gbs = bytes_per_obs() * count / (k_ms * 1e-3) * 1e-9
     roofline = {"bound": "tensor", "achieved": ach_tf, "peak": dmma.value, "unit": "TFLOP/s", "frac": ach_tf / dmma.value,
-                "traffic": None, "kernel": "dense statistics pass (X.A, X^T.Ez, Ez^T.Ez) per rank",
+                "traffic": None, "kernel": ("masked E-step + statistics (TMA/DMMA b pass, register solver, DMMA complement sums, DMMA S2 pass) per rank"
+                           if missing else "dense statistics pass (X.A, X^T.Ez, Ez^T.Ez) per rank"),
                 "kernel_ms": k_ms, "peak_source": "in-run DMMA.8x8x4 register-chain probe (no FP64 entry in MEASURED_PEAKS.json); "
                 "cublasDgemm 8192^3 measured 35.8 TFLOP/s (profiles/r1_fp64_peaks.log)",
                 "hbm_achieved_gbs": ach_gbs, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_frac": ach_gbs / peaks.get("hbm_gbs"),
@@ -285,6 +286,7 @@ def main():
             assert st.value == args.steps
             d2h = 8 * (D * M + 2)
         else:
+            R = torch.empty((D, count), dtype=torch.float64, pin_memory=True) if missing else None
             barrier()
             t0 = time.perf_counter()
             s2 = g.Session(D, n_obs, M, missing=missing, obs_begin=begin, obs_count=count)
@@ -295,7 +297,6 @@ def main():
             llv = s2.loglik()
             d2h = 8 * (D * M + 2)
             if missing:
-                R = torch.empty((D, count), dtype=torch.float64, pin_memory=True)
                 _lib.check(lib.gplvm_session_restored(s2.h, _lib.dptr(R.numpy()), count))
                 d2h += 8 * D * count
             barrier()

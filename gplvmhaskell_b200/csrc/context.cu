@@ -159,9 +159,12 @@ int ensure_context() {
   return GPLVM_OK;
 }
 
+void gp_release_workspace();
+
 int shutdown_context() {
   Context& c = ctx();
   std::lock_guard<std::recursive_mutex> lk(c.mu);
+  gp_release_workspace();
   for (Shard& s : c.shards) {
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);

@@ -29,6 +29,7 @@ constexpr int NB = 128;      // panel width == GEMM tile edge
 constexpr int KC = 16;       // K chunk staged in shared memory
 constexpr int KP = KC + 4;   // padded row stride (doubles) of a staged chunk: conflict-free fragment loads
 constexpr int STAGES = 3;
+constexpr int SB = 8;         // super-block edge (tiles) of the trailing-update rasterisation
 constexpr int GEMM_SMEM = STAGES * 2 * NB * KP * (int)sizeof(double);
 
 struct KernelSpec {      // how to generate a kernel-matrix entry on the fly
@@ -91,17 +92,27 @@ __global__ void __launch_bounds__(128) gp_first_panel_kernel(double* __restrict_
 // Shared tile Ls (nb x LDS): lower triangle = L; after the factorisation the strict upper triangle receives the
 // strictly-lower part of T = L^-1 TRANSPOSED (T[i][j], i > j, lives at Ls[j][i]); diag(T) = 1 / diag(L).
 constexpr int LDS_DIAG = NB + 1;
-constexpr int DIAG_SMEM = NB * LDS_DIAG * (int)sizeof(double);
+constexpr int DIAG_SMEM = (NB * LDS_DIAG + NB) * (int)sizeof(double);
 
 // T = L^-1 by forward substitution on e_j, one thread per column j (reads row j of the upper triangle as
-// its own history => bank-conflict free, stride LDS_DIAG between threads).
-__device__ __forceinline__ void tri_inverse_in_place(double* Ls, int nb) {
+// its own history => bank-conflict free, stride LDS_DIAG between threads).  dinv[i] = 1 / L[i][i].  Four
+// independent partial sums per entry break the FMA dependency chain.
+__device__ __forceinline__ void tri_inverse_in_place(double* Ls, int nb, const double* dinv) {
   for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-    const double tjj = 1.0 / Ls[j * LDS_DIAG + j];
+    const double tjj = dinv[j];
+    const double* hist = Ls + j * LDS_DIAG;   // hist[k] = T[k][j] for k > j
     for (int i = j + 1; i < nb; ++i) {
-      double s = -Ls[i * LDS_DIAG + j] * tjj;
-      for (int k = j + 1; k < i; ++k) s = fma(-Ls[i * LDS_DIAG + k], Ls[j * LDS_DIAG + k], s);
-      Ls[j * LDS_DIAG + i] = s / Ls[i * LDS_DIAG + i];
+      const double* Li = Ls + i * LDS_DIAG;
+      double s0 = -Li[j] * tjj, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int k = j + 1;
+      for (; k + 3 < i; k += 4) {
+        s0 = fma(-Li[k], hist[k], s0);
+        s1 = fma(-Li[k + 1], hist[k + 1], s1);
+        s2 = fma(-Li[k + 2], hist[k + 2], s2);
+        s3 = fma(-Li[k + 3], hist[k + 3], s3);
+      }
+      for (; k < i; ++k) s0 = fma(-Li[k], hist[k], s0);
+      Ls[j * LDS_DIAG + i] = ((s0 + s1) + (s2 + s3)) * dinv[i];
     }
   }
   __syncthreads();
@@ -110,23 +121,116 @@ __device__ __forceinline__ double tinv_at(const double* Ls, int i, int j) {
   return (j < i) ? Ls[j * LDS_DIAG + i] : ((i == j) ? 1.0 / Ls[i * LDS_DIAG + i] : 0.0);
 }
 
+// In-place lower Cholesky of the 128 x 128 SPD matrix in shared memory (lower triangle valid on entry; the strict
+// upper triangle is scratch), blocked by 32 columns:
+//   factor : warp 0 factors the 32 x 32 diagonal block in REGISTERS (lane c = column c, full symmetric block, so
+//            L[c][k] is read from the lane's own registers; pivot and column k travel by shuffles; rsqrt + Newton)
+//   trsm   : one thread per row below solves x L11^T = a by substitution (L11 reads are shared-memory broadcasts)
+//   syrk   : 16 x 16 threads, 6 x 6 register tiles, trailing block -= L21 L21^T
+// dinv[j] receives 1 / L[j][j].  Returns (in every thread) false when a pivot is not positive.
+__device__ inline bool block_cholesky_128(double* Ls, double* dinv, int* flag) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int LD = LDS_DIAG;
+  if (tid == 0) *flag = 1;
+  __syncthreads();
+  for (int c0 = 0; c0 < NB; c0 += 32) {
+    if (warp == 0) {
+      double m[32];
+#pragma unroll
+      for (int a = 0; a < 32; ++a) m[a] = (a >= lane) ? Ls[(c0 + a) * LD + c0 + lane] : Ls[(c0 + lane) * LD + c0 + a];
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const double pk = __shfl_sync(0xffffffffu, m[k], k);
+        ok = ok && (pk > 0.0);
+        const double y = rsqrt_nr(pk);
+        const double lck = m[k] * y;
+        if (lane == k) {
+          dinv[c0 + k] = y;
+          Ls[(c0 + k) * LD + c0 + k] = pk * y;
+        }
+#pragma unroll
+        for (int a = k + 1; a < 32; ++a) {
+          const double sa = m[a] * y;
+          if (lane == k) Ls[(c0 + a) * LD + c0 + k] = sa;
+          const double lak = __shfl_sync(0xffffffffu, sa, k);
+          m[a] = fma(-lak, lck, m[a]);
+        }
+      }
+      if (!ok && lane == 0) *flag = 0;
+    }
+    __syncthreads();
+    const int rb = NB - c0 - 32;  // rows below this block column
+    if (tid < rb) {
+      const int i = c0 + 32 + tid;
+      double x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = Ls[i * LD + c0 + j];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        double sacc = x[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) sacc = fma(-x[k], Ls[(c0 + j) * LD + c0 + k], sacc);
+        x[j] = sacc * dinv[c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Ls[i * LD + c0 + j] = x[j];
+    }
+    __syncthreads();
+    if (rb > 0) {
+      const int ty = tid >> 4, tx = tid & 15, nt = rb >> 4, base = c0 + 32;
+      double acc[6][6];
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[p][q] = 0.0;
+      for (int k = 0; k < 32; ++k) {
+        double li[6], lj[6];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          li[p] = (p < nt) ? Ls[(base + ty + 16 * p) * LD + c0 + k] : 0.0;
+          lj[p] = (p < nt) ? Ls[(base + tx + 16 * p) * LD + c0 + k] : 0.0;
+        }
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) acc[p][q] = fma(li[p], lj[q], acc[p][q]);
+      }
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int i = base + ty + 16 * p, j = base + tx + 16 * q;
+          if (p < nt && q < nt && j <= i) Ls[i * LD + j] -= acc[p][q];
+        }
+    }
+    __syncthreads();
+  }
+  return *flag != 0;
+}
+
 __global__ void __launch_bounds__(256) gp_diag_kernel(double* __restrict__ A, int64_t ld, int64_t k0, int nb, double* __restrict__ Tinv,
                                                       double* __restrict__ y, double* __restrict__ alpha, double* __restrict__ state) {
   extern __shared__ double sm[];
   double* Ls = sm;
+  double* dinv = sm + NB * LDS_DIAG;
+  __shared__ int flag;
   const int tid = threadIdx.x;
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    const int i = e / nb, j = e % nb;
-    Ls[i * LDS_DIAG + j] = (j <= i) ? A[(k0 + i) * ld + (k0 + j)] : 0.0;
+  // rows / columns past nb (last, incomplete panel) are padded with the identity
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int i = e / NB, j = e % NB;
+    double v = 0.0;
+    if (j <= i) v = (i < nb) ? A[(k0 + i) * ld + (k0 + j)] : ((i == j) ? 1.0 : 0.0);
+    Ls[i * LDS_DIAG + j] = v;
   }
   __syncthreads();
-  const bool ok = block_cholesky(Ls, nb, LDS_DIAG);
+  const bool ok = block_cholesky_128(Ls, dinv, &flag);
   for (int e = tid; e < nb * nb; e += blockDim.x) {
     const int i = e / nb, j = e % nb;
     if (j <= i) A[(k0 + i) * ld + (k0 + j)] = Ls[i * LDS_DIAG + j];
   }
   __syncthreads();
-  tri_inverse_in_place(Ls, nb);
+  tri_inverse_in_place(Ls, nb, dinv);
   for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int i = e / NB, j = e % NB;
     Tinv[e] = (i < nb && j < nb) ? tinv_at(Ls, i, j) : 0.0;
@@ -174,22 +278,27 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 1) gp_gemm_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ Apan, int64_t lda,
                                                         const double* __restrict__ Bmat, int64_t ldb, int64_t r0, int64_t N,
                                                         int64_t ccol0, int Kdim, double* __restrict__ y,
-                                                        const double* __restrict__ alpha, KernelSpec ks) {
+                                                        const double* __restrict__ alpha, KernelSpec ks, int colmode) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps; warp tile 64 x 32
 
   int64_t ti, tj;  // tile row / col (units of NB) relative to r0
-  if (MODE == MODE_PANEL) {
+  if (MODE == MODE_PANEL || colmode) {  // colmode: only the first block column of the trailing matrix
     ti = blockIdx.x; tj = 0;
   } else {
-    // triangular index: blockIdx.x = ti (ti + 1) / 2 + tj, tj <= ti
-    const int64_t b = blockIdx.x;
-    ti = (int64_t)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
-    while (ti * (ti + 1) / 2 > b) --ti;
-    tj = b - ti * (ti + 1) / 2;
+    // Super-block rasterisation for L2 reuse: tiles are visited in SB x SB groups (lower-triangular order over the
+    // groups, row-major inside a group), so that ~2 resident waves of CTAs share (SB + SB) x 256 KB of panel rows.
+    const int64_t b = blockIdx.x / (SB * SB);
+    const int local = (int)(blockIdx.x % (SB * SB));
+    int64_t bi = (int64_t)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+    while (bi * (bi + 1) / 2 > b) --bi;
+    const int64_t bj = b - bi * (bi + 1) / 2;
+    ti = bi * SB + local / SB;
+    tj = bj * SB + local % SB;
+    if (tj > ti || r0 + ti * NB >= N) return;
   }
   const int64_t row0 = r0 + ti * NB;                                   // first global row of the C tile
   const int64_t brow0 = (MODE == MODE_PANEL) ? 0 : r0 + tj * NB;      // first row of the B operand
@@ -356,13 +465,48 @@ __global__ void __launch_bounds__(256) tri_inverse_kernel(const double* __restri
     Ls[i * LDS_DIAG + j] = (j <= i) ? L[(k0 + i) * ld + (k0 + j)] : 0.0;
   }
   __syncthreads();
-  for (int j = tid; j < nb; j += blockDim.x)
+  double* dinv = sm + NB * LDS_DIAG;
+  for (int j = tid; j < nb; j += blockDim.x) {
     if (Ls[j * LDS_DIAG + j] == 0.0) state[1] = 1.0;
-  tri_inverse_in_place(Ls, nb);
+    dinv[j] = 1.0 / Ls[j * LDS_DIAG + j];
+  }
+  __syncthreads();
+  tri_inverse_in_place(Ls, nb, dinv);
   for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int i = e / NB, j = e % NB;
     Tinv[e] = (i < nb && j < nb) ? tinv_at(Ls, i, j) : 0.0;
   }
+}
+
+// Cached device workspace for the N x ld matrix (the largest request so far is kept until gplvm_dist_finalize or a
+// larger request): an 8.6 GB cudaMalloc / cudaFree pair per call costs more than the panel factorisations.
+struct Workspace {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int device = -1;
+};
+Workspace g_ws;
+
+int workspace_get(size_t bytes, int device, double** out) {
+  if (g_ws.p && (g_ws.bytes < bytes || g_ws.device != device)) {
+    cudaFree(g_ws.p);
+    g_ws = Workspace();
+  }
+  if (!g_ws.p) {
+    CUDA_TRY(cudaMalloc(&g_ws.p, bytes));
+    g_ws.bytes = bytes;
+    g_ws.device = device;
+  }
+  *out = static_cast<double*>(g_ws.p);
+  return GPLVM_OK;
+}
+
+// Leading dimension: even (16-byte aligned rows for the staged copies) and never a multiple of 256 doubles -- with a
+// power-of-two row pitch the 128 rows of a tile fall into the same L2 slice / HBM channel (partition camping).
+inline int64_t padded_ld(int64_t N) {
+  int64_t ld = round_up(N, 2);
+  if (ld % 256 == 0) ld += 16;
+  return ld;
 }
 
 struct DevBuf {
@@ -397,22 +541,42 @@ int factorise(double* dA, int64_t N, int64_t ld, const KernelSpec* gen, double* 
     const int nb0 = (int)std::min<int64_t>(NB, N);
     GP_LAUNCH(gp_first_panel_kernel, (unsigned)N, 128, 0, st, dA, ld, nb0, ks);
   }
-  for (int64_t k0 = 0; k0 < N; k0 += NB) {
-    const int nb = (int)std::min<int64_t>(NB, N - k0);
-    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, st, dA, ld, k0, nb, dTinv, dy, dalpha, dstate);
+  // Two-level blocking: outer panels of 2 NB = 256 columns.  Inside an outer panel two NB-wide inner panels are
+  // factorised (diag + panel GEMM) with one block-column update between them; the trailing matrix is then updated
+  // ONCE with K = 256, which halves the read-modify-write traffic of the big update and its epilogue overhead.
+  auto panel = [&](int64_t k0, int nb) -> int {   // L21 = A21 T^T for the rows below the diagonal block at k0
     const int64_t r0 = k0 + nb;
-    if (r0 >= N) break;
     const int64_t T = ceil_div(N - r0, NB);
-    const int Kdim = (int)round_up(nb, 4);  // nb == NB here except for the last (incomplete) panel, which has no rows below
-    GP_LAUNCH(gp_gemm_kernel<MODE_PANEL>, (unsigned)T, 256, GEMM_SMEM, st, dA, ld, dA + k0, ld, dTinv, (int64_t)NB, r0, N, k0, Kdim,
-              dy, dy ? dalpha : nullptr, ks);
-    const int64_t ntiles = T * (T + 1) / 2;
-    if (gen && k0 == 0)
-      GP_LAUNCH(gp_gemm_kernel<MODE_SYRK_GEN>, (unsigned)ntiles, 256, GEMM_SMEM, st, dA, ld, dA + k0, ld, dA + k0, ld, r0, N, 0, Kdim,
-                nullptr, nullptr, ks);
+    GP_LAUNCH(gp_gemm_kernel<MODE_PANEL>, (unsigned)T, 256, GEMM_SMEM, st, dA, ld, dA + k0, ld, dTinv, (int64_t)NB, r0, N, k0,
+              (int)round_up(nb, 4), dy, dy ? dalpha : nullptr, ks, 0);
+    return GPLVM_OK;
+  };
+  auto update = [&](int64_t kpan, int Kdim, int64_t r0, bool column_only, bool generate) -> int {
+    const int64_t T = ceil_div(N - r0, NB);
+    const int64_t nsb = ceil_div(T, SB);
+    const int64_t ntiles = column_only ? T : nsb * (nsb + 1) / 2 * SB * SB;
+    if (generate)
+      GP_LAUNCH(gp_gemm_kernel<MODE_SYRK_GEN>, (unsigned)ntiles, 256, GEMM_SMEM, st, dA, ld, dA + kpan, ld, dA + kpan, ld, r0, N, 0,
+                Kdim, nullptr, nullptr, ks, column_only ? 1 : 0);
     else
-      GP_LAUNCH(gp_gemm_kernel<MODE_SYRK>, (unsigned)ntiles, 256, GEMM_SMEM, st, dA, ld, dA + k0, ld, dA + k0, ld, r0, N, 0, Kdim,
-                nullptr, nullptr, ks);
+      GP_LAUNCH(gp_gemm_kernel<MODE_SYRK>, (unsigned)ntiles, 256, GEMM_SMEM, st, dA, ld, dA + kpan, ld, dA + kpan, ld, r0, N, 0, Kdim,
+                nullptr, nullptr, ks, column_only ? 1 : 0);
+    return GPLVM_OK;
+  };
+  for (int64_t K0 = 0; K0 < N; K0 += 2 * NB) {
+    const bool generate = gen && K0 == 0;
+    const int nb1 = (int)std::min<int64_t>(NB, N - K0);
+    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, st, dA, ld, K0, nb1, dTinv, dy, dalpha, dstate);
+    const int64_t r1 = K0 + nb1;
+    if (r1 >= N) break;
+    GP_TRY(panel(K0, nb1));
+    GP_TRY(update(K0, nb1, r1, true, generate));     // block column [r1, r1 + NB) only (K = 128)
+    const int nb2 = (int)std::min<int64_t>(NB, N - r1);
+    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, st, dA, ld, r1, nb2, dTinv, dy, dalpha, dstate);
+    const int64_t r2 = r1 + nb2;
+    if (r2 >= N) break;
+    GP_TRY(panel(r1, nb2));
+    GP_TRY(update(K0, nb1 + nb2, r2, false, generate));  // whole trailing matrix, K = 256
   }
   return GPLVM_OK;
 }
@@ -426,6 +590,12 @@ int copy_lower_to_host(double* dA, int64_t N, int64_t ld, double* L_out, cudaStr
 }
 
 }  // namespace
+
+void gp_release_workspace() {
+  if (g_ws.p) cudaFree(g_ws.p);
+  g_ws = Workspace();
+}
+
 }  // namespace gplvm
 
 using namespace gplvm;
@@ -477,10 +647,11 @@ int gplvm_gp_chol_lml(const double* X, int64_t N, int64_t Q, const double* y, co
   CUDA_TRY(cudaSetDevice(c.shards[0].device));
   cudaStream_t st = c.shards[0].stream;
   DevBuf dX, dl, dA, dy, dal, dT, dst;
-  const int64_t ld = round_up(N, 2);  // 16-byte aligned rows for the staged copies
+  const int64_t ld = padded_ld(N);
   CUDA_TRY(cudaMalloc(&dX.p, sizeof(double) * N * Q));
   CUDA_TRY(cudaMalloc(&dl.p, sizeof(double) * Q));
-  CUDA_TRY(cudaMalloc(&dA.p, sizeof(double) * (size_t)N * ld));
+  double* dAp = nullptr;
+  GP_TRY(workspace_get(sizeof(double) * (size_t)N * ld, c.shards[0].device, &dAp));
   CUDA_TRY(cudaMalloc(&dy.p, sizeof(double) * N));
   CUDA_TRY(cudaMalloc(&dal.p, sizeof(double) * N));
   CUDA_TRY(cudaMalloc(&dT.p, sizeof(double) * NB * NB));
@@ -490,7 +661,7 @@ int gplvm_gp_chol_lml(const double* X, int64_t N, int64_t Q, const double* y, co
   CUDA_TRY(cudaMemcpyAsync(dl.p, inv_lengthscale2, sizeof(double) * Q, cudaMemcpyHostToDevice, st));
   if (y) CUDA_TRY(cudaMemcpyAsync(dy.p, y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
   KernelSpec ks{dX.as<double>(), dl.as<double>(), variance, jitter, (int)Q};
-  GP_TRY(factorise(dA.as<double>(), N, ld, &ks, y ? dy.as<double>() : nullptr, dal.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  GP_TRY(factorise(dAp, N, ld, &ks, y ? dy.as<double>() : nullptr, dal.as<double>(), dT.as<double>(), dst.as<double>(), st));
   if (y) GP_LAUNCH(gp_lml_kernel, 1, 256, 0, st, dal.as<double>(), N, dst.as<double>());
   double state[8];
   CUDA_TRY(cudaMemcpyAsync(state, dst.p, sizeof state, cudaMemcpyDeviceToHost, st));
@@ -500,7 +671,7 @@ int gplvm_gp_chol_lml(const double* X, int64_t N, int64_t Q, const double* y, co
     return fail(GPLVM_ERR_NUMERIC, "gplvm_gp_chol_lml: kernel matrix not positive definite (panel %d)", (int)state[1] - 1);
   if (lml_out) *lml_out = state[3];
   if (logdet_out) *logdet_out = 2.0 * state[0];
-  if (L_out) GP_TRY(copy_lower_to_host(dA.as<double>(), N, ld, L_out, st));
+  if (L_out) GP_TRY(copy_lower_to_host(dAp, N, ld, L_out, st));
   return GPLVM_OK;
 }
 
@@ -513,7 +684,7 @@ int gplvm_cholesky(const double* A, int64_t N, double* L_out) {
   CUDA_TRY(cudaSetDevice(c.shards[0].device));
   cudaStream_t st = c.shards[0].stream;
   DevBuf dA, dT, dst;
-  const int64_t ld = round_up(N, 2);
+  const int64_t ld = padded_ld(N);
   CUDA_TRY(cudaMalloc(&dA.p, sizeof(double) * (size_t)N * ld));
   CUDA_TRY(cudaMalloc(&dT.p, sizeof(double) * NB * NB));
   CUDA_TRY(cudaMalloc(&dst.p, sizeof(double) * 8));

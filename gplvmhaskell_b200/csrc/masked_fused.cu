@@ -26,18 +26,6 @@ constexpr int NVF = MF * (MF + 1) / 2;   // 136
 constexpr int EASF = NVF + MF;           // 152
 constexpr int WP = 18;                   // pitch (doubles) of the W rows in shared memory: spreads gathered rows over the banks
 
-// 1 / x for a positive normal x: hardware seed + 2 Newton steps (relative error ~ 1 ulp)
-__device__ __forceinline__ double rcp_nr(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-  }
-  return y;
-}
-
 // LL = false: writes EA[n] = [vech A_i | ez_i].   LL = true: accumulates the per-observation likelihood terms
 //   cnt log 2pi + (cnt - M) log s2 + log det M_i + (yy_i - b_i . ez_i) / s2      into partials[blockIdx.x].
 template <int DD, bool LL>
