@@ -72,5 +72,24 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CLI_SRC = os.path.join(HERE, "..", "cli", "gplvmhaskell_exe.cpp")
+CLI = os.path.join(HERE, "GPLVMHaskell-exe")
+
+
+def build_cli(force: bool = False) -> str:
+    """g++ the GPLVMHaskell-exe twin (cli/gplvmhaskell_exe.cpp) against the in-tree library (rpath $ORIGIN)."""
+    lib = build_library()
+    if (not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= os.path.getmtime(CLI_SRC)
+            and os.path.getmtime(CLI) >= os.path.getmtime(lib)):
+        return CLI
+    cmd = ["g++", "-O2", "-std=c++17", CLI_SRC, "-o", CLI, "-L" + HERE, "-lgplvm_b200", "-Wl,-rpath,$ORIGIN",
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for the CLI twin:\n%s\n%s" % (r.stdout, r.stderr))
+    return CLI
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cli(force="--force" in sys.argv))

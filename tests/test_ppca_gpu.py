@@ -257,3 +257,24 @@ def test_missing_large_properties():
     obs = ~np.isnan(Y)
     rmse = float(np.sqrt(np.mean((R[obs] - Y[obs]) ** 2)))
     assert 0.5 < rmse < 1.2
+
+
+# ---------------------------------------------------------------------------------------------------
+# N > 1 GPUs in one process (skipped on a single-GPU box; the gloo test covers the host logic on CPU)
+# ---------------------------------------------------------------------------------------------------
+
+def test_two_gpus_match_one_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    lib = g.load_library()
+    res = []
+    try:
+        for ngpu in (1, 2):
+            _lib.check(lib.gplvm_set_devices(ngpu))
+            Y, W0 = synth(256, 5000, 16, seed=21, nan_prob=0.2)
+            res.append(g.em_steps_missed(Y, W0, 1.0, g.Left(3)))
+    finally:
+        _lib.check(lib.gplvm_set_devices(1))
+    assert rel(res[1][0], res[0][0]) < 1e-11 and abs(res[1][1] - res[0][1]) < 1e-12 * res[0][1]
+    assert rel(res[1][3], res[0][3]) < 1e-10
