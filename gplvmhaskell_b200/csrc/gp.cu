@@ -29,8 +29,8 @@ constexpr int NB = 128;      // panel width == GEMM tile edge
 constexpr int KC = 16;       // K chunk staged in shared memory
 constexpr int KP = KC + 4;   // padded row stride (doubles) of a staged chunk: conflict-free fragment loads
 constexpr int STAGES = 3;
-constexpr int SB = 8;         // super-block edge (tiles) of the trailing-update rasterisation
-constexpr int GEMM_SMEM = STAGES * 2 * NB * KP * (int)sizeof(double);
+constexpr int GEMM_SMEM = STAGES * 2 * NB * KP * (int)sizeof(double);          // 128 x 128 tiles (panel)
+constexpr int SYRK_SMEM = STAGES * (NB + 64) * KP * (int)sizeof(double);       // 128 x 64 tiles (trailing update)
 
 struct KernelSpec {      // how to generate a kernel-matrix entry on the fly
   const double* X;       // N x Q row-major inputs (device)
@@ -270,53 +270,59 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 enum GemmMode { MODE_PANEL = 0, MODE_SYRK = 1, MODE_SYRK_GEN = 2 };
 
 // MODE_PANEL : rows [r0, N) of the panel: C = A . B^T, A = C's own panel columns (in place), B = Tinv (NB x NB);
-//              one CTA per 128-row strip; also y[i] -= sum_j C[i][j] alpha[j].
-// MODE_SYRK  : trailing matrix, lower tiles: C -= A . B^T with A = panel rows of tile-row, B = panel rows of tile-col.
+//              one CTA per 128-row strip (TN = 128); also y[i] -= sum_j C[i][j] alpha[j].
+// MODE_SYRK  : trailing matrix, lower tiles: C -= A . B^T with A = panel rows of the tile's rows, B = panel rows of the
+//              tile's columns.  128 x 64 tiles (TN = 64), 2 CTAs per SM so that one CTA's read-modify-write epilogue
+//              hides under the other's MMA loop.
 // MODE_SYRK_GEN: as SYRK but C is generated from the kernel function instead of being read.
-// All row indices are global; `Kdim` = panel width actually used (multiple of 4, <= NB); A/B rows have leading dim lda/ldb.
-template <int MODE>
-__global__ void __launch_bounds__(256, 1) gp_gemm_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ Apan, int64_t lda,
-                                                        const double* __restrict__ Bmat, int64_t ldb, int64_t r0, int64_t N,
-                                                        int64_t ccol0, int Kdim, double* __restrict__ y,
-                                                        const double* __restrict__ alpha, KernelSpec ks, int colmode) {
+// All row indices are global; `Kdim` = panel width (multiple of 4); A/B rows have leading dimensions lda/ldb.
+// Tile numbering (SYRK): tile row ti covers rows r0 + 128 ti ..., tile column tj covers columns r0 + 64 tj ...;
+// row ti has the 2 ti + 2 column tiles that touch the lower triangle => linear index b = ti (ti + 1) + tj.
+// colmode: only the first 128-column block column (two column tiles) of the trailing matrix.
+template <int MODE, int TN>
+__global__ void __launch_bounds__(256, (TN == 64) ? 2 : 1)
+    gp_gemm_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ Apan, int64_t lda, const double* __restrict__ Bmat,
+                   int64_t ldb, int64_t r0, int64_t N, int64_t ccol0, int Kdim, double* __restrict__ y,
+                   const double* __restrict__ alpha, KernelSpec ks, int colmode) {
+  constexpr int WN_WARPS = TN / 32;            // 4 | 2
+  constexpr int WM_WARPS = 8 / WN_WARPS;       // 2 | 4
+  constexpr int WROWS = NB / WM_WARPS;         // 64 | 32 rows per warp
+  constexpr int MT = WROWS / 8;                // 8 | 4 m-tiles per warp (4 n-tiles always)
+  constexpr int STAGE_D = (NB + TN) * KP;      // doubles per stage
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps; warp tile 64 x 32
+  const int wm = warp / WN_WARPS, wn = warp % WN_WARPS;
 
-  int64_t ti, tj;  // tile row / col (units of NB) relative to r0
-  if (MODE == MODE_PANEL || colmode) {  // colmode: only the first block column of the trailing matrix
+  int64_t ti, tj;
+  if (MODE == MODE_PANEL) {
     ti = blockIdx.x; tj = 0;
+  } else if (colmode) {
+    ti = blockIdx.x >> 1; tj = blockIdx.x & 1;
   } else {
-    // Super-block rasterisation for L2 reuse: tiles are visited in SB x SB groups (lower-triangular order over the
-    // groups, row-major inside a group), so that ~2 resident waves of CTAs share (SB + SB) x 256 KB of panel rows.
-    const int64_t b = blockIdx.x / (SB * SB);
-    const int local = (int)(blockIdx.x % (SB * SB));
-    int64_t bi = (int64_t)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
-    while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
-    while (bi * (bi + 1) / 2 > b) --bi;
-    const int64_t bj = b - bi * (bi + 1) / 2;
-    ti = bi * SB + local / SB;
-    tj = bj * SB + local % SB;
-    if (tj > ti || r0 + ti * NB >= N) return;
+    const int64_t b = blockIdx.x;
+    ti = (int64_t)((sqrt(4.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) <= b) ++ti;
+    while (ti * (ti + 1) > b) --ti;
+    tj = b - ti * (ti + 1);
   }
   const int64_t row0 = r0 + ti * NB;                                   // first global row of the C tile
-  const int64_t brow0 = (MODE == MODE_PANEL) ? 0 : r0 + tj * NB;      // first row of the B operand
-  const int64_t col0 = (MODE == MODE_PANEL) ? ccol0 : r0 + tj * NB;   // first global column of the C tile
+  const int64_t brow0 = (MODE == MODE_PANEL) ? 0 : r0 + tj * TN;      // first row of the B operand
+  const int64_t col0 = (MODE == MODE_PANEL) ? ccol0 : r0 + tj * TN;   // first global column of the C tile
   const int64_t brows = (MODE == MODE_PANEL) ? NB : N;                // rows available in B
 
-  double acc[8][4][2];
+  double acc[MT][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int nchunks = (Kdim + KC - 1) / KC;
   auto load_chunk = [&](int c, int stage) {
-    double* As = smem + (size_t)stage * 2 * NB * KP;
+    double* As = smem + (size_t)stage * STAGE_D;
     double* Bs = As + NB * KP;
     const int kc0 = c * KC;
-    // 128 rows x 16 doubles = 128 x 8 16-byte pieces per operand; 256 threads -> 4 pieces each per operand
+    // rows x 16 doubles = rows x 8 16-byte pieces; 256 threads -> 4 pieces each for A (128 rows), TN / 32 for B
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int e = tid + it * 256;
@@ -326,9 +332,11 @@ __global__ void __launch_bounds__(256, 1) gp_gemm_kernel(double* __restrict__ C,
       const int64_t ar = row0 + r;
       const bool pa = kin && ar < N;
       cp_async16(As + r * KP + p * 2, Apan + (pa ? ar * lda + kk : 0), pa);
-      const int64_t br = brow0 + r;
-      const bool pb = kin && br < brows;
-      cp_async16(Bs + r * KP + p * 2, Bmat + (pb ? br * ldb + kk : 0), pb);
+      if (it < TN / 32) {
+        const int64_t br = brow0 + r;
+        const bool pb = kin && br < brows;
+        cp_async16(Bs + r * KP + p * 2, Bmat + (pb ? br * ldb + kk : 0), pb);
+      }
     }
   };
 
@@ -345,17 +353,17 @@ __global__ void __launch_bounds__(256, 1) gp_gemm_kernel(double* __restrict__ C,
       if (cn < nchunks) load_chunk(cn, cn % STAGES);
       cp_async_commit();
     }
-    const double* As = smem + (size_t)(c % STAGES) * 2 * NB * KP;
+    const double* As = smem + (size_t)(c % STAGES) * STAGE_D;
     const double* Bs = As + NB * KP;
 #pragma unroll
     for (int k4 = 0; k4 < KC; k4 += 4) {
-      double af[8], bf[4];
+      double af[MT], bf[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = As[(wm * 64 + i * 8 + g) * KP + k4 + t];
+      for (int i = 0; i < MT; ++i) af[i] = As[(wm * WROWS + i * 8 + g) * KP + k4 + t];
 #pragma unroll
       for (int j = 0; j < 4; ++j) bf[j] = Bs[(wn * 32 + j * 8 + g) * KP + k4 + t];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
@@ -363,13 +371,13 @@ __global__ void __launch_bounds__(256, 1) gp_gemm_kernel(double* __restrict__ C,
   cp_async_wait<0>();
   __syncthreads();  // every warp is done reading the staged operands (PANEL writes C == A in place)
 
-  // epilogue: thread owns C[row0 + wm*64 + i*8 + g][col0 + wn*32 + j*8 + 2t + {0,1}]
-  double ydot[8];
+  // epilogue: thread owns C[row0 + wm*WROWS + i*8 + g][col0 + wn*32 + j*8 + 2t + {0,1}]
+  double ydot[MT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ydot[i] = 0.0;
+  for (int i = 0; i < MT; ++i) ydot[i] = 0.0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t r = row0 + wm * 64 + i * 8 + g;
+  for (int i = 0; i < MT; ++i) {
+    const int64_t r = row0 + wm * WROWS + i * 8 + g;
     if (r >= N) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -403,7 +411,7 @@ __global__ void __launch_bounds__(256, 1) gp_gemm_kernel(double* __restrict__ C,
     // y[r] -= sum over the 4 column-warps and the 4 lanes of a quad: shared-memory reduction, fixed order
     double* red = smem;  // 128 rows x 16 partial sums (4 wn x 4 t)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) red[(wm * 64 + i * 8 + g) * 16 + wn * 4 + t] = ydot[i];
+    for (int i = 0; i < MT; ++i) red[(wm * WROWS + i * 8 + g) * 16 + wn * 4 + t] = ydot[i];
     __syncthreads();
     if (tid < NB) {
       const int64_t r = row0 + tid;
@@ -509,6 +517,23 @@ inline int64_t padded_ld(int64_t N) {
   return ld;
 }
 
+// second (high-priority) stream and events of the look-ahead factorisation, one set per device
+int lookahead_resources(cudaStream_t* sp, cudaEvent_t* e0, cudaEvent_t* e1, cudaEvent_t* e2) {
+  struct Res { cudaStream_t s = nullptr; cudaEvent_t e[3] = {nullptr, nullptr, nullptr}; };
+  static Res res[64];
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  Res& r = res[dev & 63];
+  if (!r.s) {
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&r.s, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreateWithFlags(&r.e[i], cudaEventDisableTiming));
+  }
+  *sp = r.s; *e0 = r.e[0]; *e1 = r.e[1]; *e2 = r.e[2];
+  return GPLVM_OK;
+}
+
 struct DevBuf {
   void* p = nullptr;
   ~DevBuf() { if (p) cudaFree(p); }
@@ -518,9 +543,11 @@ struct DevBuf {
 int set_gemm_attrs() {
   static bool done = false;
   if (done) return GPLVM_OK;
-  CUDA_TRY(cudaFuncSetAttribute(gp_gemm_kernel<MODE_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  CUDA_TRY(cudaFuncSetAttribute(gp_gemm_kernel<MODE_SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  CUDA_TRY(cudaFuncSetAttribute(gp_gemm_kernel<MODE_SYRK_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute((gp_gemm_kernel<MODE_PANEL, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute((gp_gemm_kernel<MODE_SYRK, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute((gp_gemm_kernel<MODE_SYRK_GEN, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute((gp_gemm_kernel<MODE_SYRK, 64>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUDA_TRY(cudaFuncSetAttribute((gp_gemm_kernel<MODE_SYRK_GEN, 64>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const int diag_smem = DIAG_SMEM;
   CUDA_TRY(cudaFuncSetAttribute(gp_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
   CUDA_TRY(cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
@@ -544,40 +571,63 @@ int factorise(double* dA, int64_t N, int64_t ld, const KernelSpec* gen, double* 
   // Two-level blocking: outer panels of 2 NB = 256 columns.  Inside an outer panel two NB-wide inner panels are
   // factorised (diag + panel GEMM) with one block-column update between them; the trailing matrix is then updated
   // ONCE with K = 256, which halves the read-modify-write traffic of the big update and its epilogue overhead.
-  auto panel = [&](int64_t k0, int nb) -> int {   // L21 = A21 T^T for the rows below the diagonal block at k0
+  auto panel = [&](cudaStream_t sx, int64_t k0, int nb) -> int {   // L21 = A21 T^T for the rows below the diagonal block at k0
     const int64_t r0 = k0 + nb;
     const int64_t T = ceil_div(N - r0, NB);
-    GP_LAUNCH(gp_gemm_kernel<MODE_PANEL>, (unsigned)T, 256, GEMM_SMEM, st, dA, ld, dA + k0, ld, dTinv, (int64_t)NB, r0, N, k0,
+    GP_LAUNCH((gp_gemm_kernel<MODE_PANEL, 128>), (unsigned)T, 256, GEMM_SMEM, sx, dA, ld, dA + k0, ld, dTinv, (int64_t)NB, r0, N, k0,
               (int)round_up(nb, 4), dy, dy ? dalpha : nullptr, ks, 0);
     return GPLVM_OK;
   };
-  auto update = [&](int64_t kpan, int Kdim, int64_t r0, bool column_only, bool generate) -> int {
+  auto update = [&](cudaStream_t sx, int64_t kpan, int Kdim, int64_t r0, bool column_only, bool generate) -> int {
     const int64_t T = ceil_div(N - r0, NB);
-    const int64_t nsb = ceil_div(T, SB);
-    const int64_t ntiles = column_only ? T : nsb * (nsb + 1) / 2 * SB * SB;
+    const int64_t ntiles = column_only ? 2 * T : T * (T + 1);
     if (generate)
-      GP_LAUNCH(gp_gemm_kernel<MODE_SYRK_GEN>, (unsigned)ntiles, 256, GEMM_SMEM, st, dA, ld, dA + kpan, ld, dA + kpan, ld, r0, N, 0,
+      GP_LAUNCH((gp_gemm_kernel<MODE_SYRK_GEN, 64>), (unsigned)ntiles, 256, SYRK_SMEM, sx, dA, ld, dA + kpan, ld, dA + kpan, ld, r0, N, 0,
                 Kdim, nullptr, nullptr, ks, column_only ? 1 : 0);
     else
-      GP_LAUNCH(gp_gemm_kernel<MODE_SYRK>, (unsigned)ntiles, 256, GEMM_SMEM, st, dA, ld, dA + kpan, ld, dA + kpan, ld, r0, N, 0, Kdim,
+      GP_LAUNCH((gp_gemm_kernel<MODE_SYRK, 64>), (unsigned)ntiles, 256, SYRK_SMEM, sx, dA, ld, dA + kpan, ld, dA + kpan, ld, r0, N, 0, Kdim,
                 nullptr, nullptr, ks, column_only ? 1 : 0);
     return GPLVM_OK;
   };
+  // Look-ahead over two streams.  `sp` (high priority) runs the latency-bound panel work of outer step k + 1 (two
+  // diagonal blocks, two panel GEMMs, one block-column update) and the "head" of update k (the next 256 columns);
+  // `st` runs the "tail" of update k (everything right of the head) -- the bulk of the flops -- back to back.
+  //   head(k) needs tail(k-1) (same region) and panel(k);  tail(k) needs panel(k) and tail(k-1);
+  //   panel(k+1) needs head(k) only, so it hides under tail(k).
+  cudaStream_t sp = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_tail = nullptr, ev_start = nullptr;
+  GP_TRY(lookahead_resources(&sp, &ev_panel, &ev_tail, &ev_start));
+  CUDA_TRY(cudaEventRecord(ev_start, st));
+  CUDA_TRY(cudaStreamWaitEvent(sp, ev_start, 0));
+  bool tail_pending = false;
   for (int64_t K0 = 0; K0 < N; K0 += 2 * NB) {
     const bool generate = gen && K0 == 0;
     const int nb1 = (int)std::min<int64_t>(NB, N - K0);
-    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, st, dA, ld, K0, nb1, dTinv, dy, dalpha, dstate);
+    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, sp, dA, ld, K0, nb1, dTinv, dy, dalpha, dstate);
     const int64_t r1 = K0 + nb1;
     if (r1 >= N) break;
-    GP_TRY(panel(K0, nb1));
-    GP_TRY(update(K0, nb1, r1, true, generate));     // block column [r1, r1 + NB) only (K = 128)
+    GP_TRY(panel(sp, K0, nb1));
+    GP_TRY(update(sp, K0, nb1, r1, true, generate));     // block column [r1, r1 + NB) only (K = 128)
     const int nb2 = (int)std::min<int64_t>(NB, N - r1);
-    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, st, dA, ld, r1, nb2, dTinv, dy, dalpha, dstate);
+    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, sp, dA, ld, r1, nb2, dTinv, dy, dalpha, dstate);
     const int64_t r2 = r1 + nb2;
     if (r2 >= N) break;
-    GP_TRY(panel(r1, nb2));
-    GP_TRY(update(K0, nb1 + nb2, r2, false, generate));  // whole trailing matrix, K = 256
+    GP_TRY(panel(sp, r1, nb2));
+    CUDA_TRY(cudaEventRecord(ev_panel, sp));
+    // head: the two block columns [r2, r2 + 128) and [r2 + 128, r2 + 256), K = 256
+    if (tail_pending) CUDA_TRY(cudaStreamWaitEvent(sp, ev_tail, 0));
+    GP_TRY(update(sp, K0, nb1 + nb2, r2, true, generate));
+    if (r2 + NB < N) GP_TRY(update(sp, K0, nb1 + nb2, r2 + NB, true, generate));
+    // tail: the trailing matrix right of the head
+    if (r2 + 2 * NB < N) {
+      CUDA_TRY(cudaStreamWaitEvent(st, ev_panel, 0));
+      GP_TRY(update(st, K0, nb1 + nb2, r2 + 2 * NB, false, generate));
+      CUDA_TRY(cudaEventRecord(ev_tail, st));
+      tail_pending = true;
+    }
   }
+  CUDA_TRY(cudaEventRecord(ev_panel, sp));
+  CUDA_TRY(cudaStreamWaitEvent(st, ev_panel, 0));  // later work on `st` (LML, copies) sees the whole factor
   return GPLVM_OK;
 }
 
