@@ -5,11 +5,11 @@
 // Reference: emStepsMissed.stepOne, src/GPLVM/PPCA.hs:106-117 (M_i = sigma^2 I + W_i^T W_i, invMP, expXi) and the
 // per-observation log-likelihood terms of PPCA.hs:149-159 (through the determinant lemma).
 //
-// Mapping: one warp per PAIR of observations.
+// Mapping: one warp per group of 8 observations.
 //   build    : M_i = C0 - W_miss^T W_miss (complement form: work ~ #missing).  The missing-feature indices are compacted
 //              from the packed mask bits; the Gram matrix is a K-compacted mma.sync.m8n8k4.f64 product whose operands
 //              are gathered rows of W in shared memory (W is D x 16, pitch 18 doubles).
-//   then one HALF-WARP per observation, lane c (0..15) owns column c of the symmetric 16 x 16 matrix in 16 registers:
+//   then one QUAD of lanes per observation, each lane owning 4 columns of the symmetric 16 x 16 matrix in registers:
 //   invert   : 16 symmetric sweeps (Gauss-Jordan on the SPD matrix, pivots = Schur complements > 0) turn the
 //              registers into -M_i^-1; lane c reads M[k][c] from its OWN column by symmetry, only column k travels
 //              by __shfl_sync; reciprocals by rcp.approx.f64 + 2 Newton steps; log det M_i = sum log pivots.
@@ -28,17 +28,29 @@ constexpr int WP = 18;                   // pitch (doubles) of the W rows in sha
 
 // LL = false: writes EA[n] = [vech A_i | ez_i].   LL = true: accumulates the per-observation likelihood terms
 //   cnt log 2pi + (cnt - M) log s2 + log det M_i + (yy_i - b_i . ez_i) / s2      into partials[blockIdx.x].
+//
+// One warp handles 8 observations at a time.  During the sweeps a QUAD of lanes owns one observation: lane j of the
+// quad holds columns j, j+4, j+8, j+12 of the symmetric 16 x 16 matrix (4 x 16 registers), so one 64-bit shuffle
+// moves a column entry for 8 observations at once (4x fewer shuffle wavefronts per observation than a half-warp
+// per observation -- the shared-memory/shuffle data pipe is what bounds this kernel).
+constexpr int LPR = 8;                          // lanes per observation during the sweeps (4: quad, 8: oct)
+constexpr int CPL = MF / LPR;                   // matrix columns per lane
+constexpr int SOLVE_ROWS = 32 / LPR;            // observations per warp
+constexpr int SOLVE_MINB = (LPR == 8) ? 2 : 1;  // CTAs per SM (register budget: CPL x 16 doubles per lane for the matrix)
+constexpr int MS_STRIDE = MF * 17 + 4;          // doubles per staged matrix; +4 spreads the lane groups over the banks
+
 template <int DD, bool LL>
-__global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ yy,
+__global__ void __launch_bounds__(256, SOLVE_MINB) masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ yy,
                                                              const uint32_t* __restrict__ mbits, int64_t n_obs, Par p,
                                                              double* __restrict__ EA, double* __restrict__ partials) {
   constexpr int WPRT = DD / 32;
+  static_assert(WPRT <= 8, "mask words per observation");
   if (!LL && p.scal[S_DONE] != 0.0) return;
   extern __shared__ double sm[];
   double* Ws = sm;                               // (DD + 1) x WP : rows of W, pitch 18 doubles; row DD = 0 (list padding)
   double* C0s = Ws + (DD + 1) * WP;              // 16 x 16 : s2 I + W^T W  (kept in p.Minv by the masked prep kernel)
-  double* Msm = C0s + MF * MF;                   // per warp: 2 x 16 x 17 staging of the two W_miss^T W_miss matrices
-  uint16_t* lists = reinterpret_cast<uint16_t*>(Msm + 8 * 2 * MF * 17);  // per warp: 2 x DD missing-feature indices
+  double* Msm = C0s + MF * MF;                   // per warp: SOLVE_ROWS staged W_miss^T W_miss matrices; the index
+  uint16_t* lists = reinterpret_cast<uint16_t*>(Msm);  // lists (SOLVE_ROWS x DD uint16) alias them (dead after the Gram loop)
   __shared__ double red[40];
   for (int e = threadIdx.x; e < (DD + 1) * MF; e += blockDim.x) {
     const int d = e >> 4, a = e & 15;
@@ -46,134 +58,182 @@ __global__ void __launch_bounds__(256, 2) masked_solve_kernel(const double* __re
   }
   for (int e = threadIdx.x; e < MF * MF; e += blockDim.x) C0s[e] = p.Minv[e];
   __syncthreads();
-  const int warp = threadIdx.x >> 5;
-  double* Mw = Msm + warp * (2 * MF * 17);
-  uint16_t* lst = lists + warp * (2 * DD);
-  const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
   const double s2 = p.scal[S_SIGMA2];
-  const int lane = threadIdx.x & 31, c = lane & 15;
-  constexpr unsigned hmask = 0xffffffffu;  // both half-warps run every shuffle together (width 16 keeps them apart)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;         // MMA fragment coordinates
+  const int rw = lane / LPR, j = lane % LPR;     // sweep coordinates: observation within the warp, lane within its group
+  double* Mw = Msm + warp * (SOLVE_ROWS * MS_STRIDE);
+  uint16_t* lst = reinterpret_cast<uint16_t*>(Mw);
+  static_assert(SOLVE_ROWS * MS_STRIDE * 8 >= SOLVE_ROWS * 256 * 2, "index lists must fit in the staging area");
+  constexpr unsigned FULL = 0xffffffffu;
   // The trip count depends on blockIdx only, so the compiler can see that every warp stays converged around the
-  // shuffles (a warp whose pair lies past the end recomputes the last observation and stores nothing).
-  const int64_t cta0 = (int64_t)blockIdx.x * 16;            // 8 warps x 2 observations per CTA and iteration
-  const int64_t stride = (int64_t)gridDim.x * 16;
+  // shuffles (a warp whose observations lie past the end recomputes the last one and stores nothing).
+  const int64_t cta0 = (int64_t)blockIdx.x * (8 * SOLVE_ROWS);
+  const int64_t stride = (int64_t)gridDim.x * (8 * SOLVE_ROWS);
   const int64_t iters = (n_obs > cta0) ? (n_obs - cta0 + stride - 1) / stride : 0;
-  const int wpair = (threadIdx.x >> 5) * 2;
   double llacc = 0.0;
   const double log2pi = 1.8378770664093453, logs2 = LL ? log(s2) : 0.0;
 
   for (int64_t it = 0; it < iters; ++it) {
-    const int64_t nb = cta0 + it * stride + wpair;
-    const bool valid = nb + (lane >> 4) < n_obs;
-    const int64_t n = valid ? nb + (lane >> 4) : n_obs - 1;
-    // ---- build M_i = C0 - W_miss^T W_miss on the tensor cores -------------------------------------------------
-    // (a) compact the missing-feature indices of the warp's two observations (ballot-free: every lane tests its own
-    //     bit of each mask word and ranks itself with a popcount); (b) K-compacted Gram matrices: k runs over the
-    //     MISSING features only, 4 per mma.sync.m8n8k4, gathered rows of W as both operands (3 tiles: 00, 01, 11);
-    //     (c) through shared memory into the column-per-lane layout of the sweeps.
-    const uint32_t mw = (c < WPRT) ? mbits[n * WPRT + c] : 0u;
-    const double bc = bsrc[n * MF + c];
-    int cnt0 = 0, cnt1 = 0;
-#pragma unroll
-    for (int wd = 0; wd < WPRT; ++wd) {
-      const uint32_t b0 = __shfl_sync(hmask, mw, wd);
-      const uint32_t b1 = __shfl_sync(hmask, mw, 16 + wd);
-      const uint32_t lt = (1u << lane) - 1u;
-      if ((b0 >> lane) & 1u) lst[cnt0 + __popc(b0 & lt)] = (uint16_t)(wd * 32 + lane);
-      if ((b1 >> lane) & 1u) lst[DD + cnt1 + __popc(b1 & lt)] = (uint16_t)(wd * 32 + lane);
-      cnt0 += __popc(b0);
-      cnt1 += __popc(b1);
-    }
-    const int nmiss = (lane & 16) ? cnt1 : cnt0;
-    const int nks = (max(cnt0, cnt1) + 3) >> 2;
-    for (int e = lane; e < nks * 4; e += 32) {  // pad with the zero row of Ws
-      if (e >= cnt0) lst[e] = (uint16_t)DD;
-      if (e >= cnt1) lst[DD + e] = (uint16_t)DD;
-    }
-    __syncwarp();
-    double g00[2][2], g01[2][2], g11[2][2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) g00[h][0] = g00[h][1] = g01[h][0] = g01[h][1] = g11[h][0] = g11[h][1] = 0.0;
-    for (int ks = 0; ks < nks; ++ks) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int d = lst[h * DD + ks * 4 + t];
-        const double f0 = Ws[d * WP + g], f1 = Ws[d * WP + 8 + g];
-        dmma(g00[h], f0, f0);
-        dmma(g01[h], f0, f1);
-        dmma(g11[h], f1, f1);
+    const int64_t nb = cta0 + it * stride + warp * SOLVE_ROWS;   // first observation of this warp
+    // ---- (a) compact the missing-feature indices of the 8 observations ---------------------------------------
+    uint32_t mwa = 0u, mwb = 0u;   // lane l: word (l & 7) of observation nb + (l >> 3) [+ 4]
+    if ((lane & 7) < WPRT) {
+      const int64_t na = min(nb + (lane >> 3), n_obs - 1);
+      mwa = mbits[na * WPRT + (lane & 7)];
+      if (SOLVE_ROWS > 4) {
+        const int64_t nc = min(nb + 4 + (lane >> 3), n_obs - 1);
+        mwb = mbits[nc * WPRT + (lane & 7)];
       }
     }
+    int cnt[SOLVE_ROWS];
+    const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      double* Mh = Mw + h * (MF * 17);
+    for (int r = 0; r < SOLVE_ROWS; ++r) {
+      int cr = 0;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        Mh[g * 17 + 2 * t + q] = g00[h][q];
-        Mh[g * 17 + 8 + 2 * t + q] = g01[h][q];
-        Mh[(8 + 2 * t + q) * 17 + g] = g01[h][q];
-        Mh[(8 + g) * 17 + 8 + 2 * t + q] = g11[h][q];
+      for (int wd = 0; wd < WPRT; ++wd) {
+        const uint32_t bits = __shfl_sync(FULL, (r < 4) ? mwa : mwb, (r & 3) * 8 + wd);
+        if ((bits >> lane) & 1u) lst[r * DD + cr + __popc(bits & lt)] = (uint16_t)(wd * 32 + lane);
+        cr += __popc(bits);
       }
+      cnt[r] = cr;
     }
+    int cmax = 0;
+#pragma unroll
+    for (int r = 0; r < SOLVE_ROWS; ++r) cmax = max(cmax, cnt[r]);
+    const int nks = (cmax + 3) >> 2;
+#pragma unroll
+    for (int r = 0; r < SOLVE_ROWS; ++r)
+      for (int e = cnt[r] + lane; e < nks * 4; e += 32) lst[r * DD + e] = (uint16_t)DD;   // pad with the zero row of Ws
     __syncwarp();
-    double m[MF];
+    // ---- (b) K-compacted Gram matrices W_miss^T W_miss on the tensor cores (tiles 00, 01, 11 per observation) ----
     {
-      const double* Mh = Mw + (lane >> 4) * (MF * 17);
+      double g00[SOLVE_ROWS][2], g01[SOLVE_ROWS][2], g11[SOLVE_ROWS][2];
 #pragma unroll
-      for (int a = 0; a < MF; ++a) m[a] = C0s[a * MF + c] - Mh[a * 17 + c];
+      for (int r = 0; r < SOLVE_ROWS; ++r) g00[r][0] = g00[r][1] = g01[r][0] = g01[r][1] = g11[r][0] = g11[r][1] = 0.0;
+      for (int ks = 0; ks < nks; ++ks) {
+#pragma unroll
+        for (int r = 0; r < SOLVE_ROWS; ++r) {
+          const int d = lst[r * DD + ks * 4 + t];
+          const double f0 = Ws[d * WP + g], f1 = Ws[d * WP + 8 + g];
+          dmma(g00[r], f0, f0);
+          dmma(g01[r], f0, f1);
+          dmma(g11[r], f1, f1);
+        }
+      }
+      __syncwarp();   // the index lists (aliased by the staging area) are dead from here on
+#pragma unroll
+      for (int r = 0; r < SOLVE_ROWS; ++r) {
+        double* Mh = Mw + r * MS_STRIDE;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          Mh[g * 17 + 2 * t + q] = g00[r][q];
+          Mh[g * 17 + 8 + 2 * t + q] = g01[r][q];
+          Mh[(8 + 2 * t + q) * 17 + g] = g01[r][q];
+          Mh[(8 + g) * 17 + 8 + 2 * t + q] = g11[r][q];
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (c) quad layout: m[q][a] = M[a][j + 4 q] = C0 - Gram ------------------------------------------------------
+    const bool valid = nb + rw < n_obs;
+    const int64_t n = valid ? nb + rw : n_obs - 1;
+    int nmiss = 0;
+#pragma unroll
+    for (int r = 0; r < SOLVE_ROWS; ++r) nmiss = (rw == r) ? cnt[r] : nmiss;
+    double m[CPL][MF];
+    {
+      const double* Mh = Mw + rw * MS_STRIDE;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q)
+#pragma unroll
+        for (int a = 0; a < MF; ++a) m[q][a] = C0s[a * MF + j + LPR * q] - Mh[a * 17 + j + LPR * q];
     }
     __syncwarp();
     // every feature missing: unsupported by the reference (Util.hs:81); flagged, outputs zeroed below
     const bool empty = nmiss >= DD;
-    if (empty && c == 0) set_err(p.scal, 2.0);
-    // ---- in-place inverse by symmetric sweeps: after sweeping k = 0..15 the matrix is -M_i^-1 ------------------
-    // Step k (pivot p = M[k][k], d = 1/p):  B[i][j] = M[i][j] - M[i][k] M[k][j] d,  B[i][k] = M[i][k] d,  B[k][k] = -d.
-    // Lane c reads M[k][c] from its own column by symmetry; only column k travels (shuffles from lane k).  Lane k's
-    // own column is kept UNSCALED with the factor d remembered in `scale` (applied once at the end), which keeps the
-    // update formula identical in every lane (r = 0 makes it a no-op in lane k) -- no per-entry selects.
+    if (empty && j == 0) set_err(p.scal, 2.0);
+    // ---- (d) in-place inverse by symmetric sweeps: after sweeping k = 0..15 the matrix is -M_i^-1 ------------------
+    // Step k (pivot p = M[k][k], d = 1/p):  B[i][l] = M[i][l] - M[i][k] M[k][l] d,  B[i][k] = M[i][k] d,  B[k][k] = -d.
+    // A lane reads M[k][c] from its own columns by symmetry; only column k travels (width-4 shuffles from its owner).
+    // The owner keeps column k UNSCALED and remembers d in `scale` (applied once at the end), which keeps the update
+    // formula identical in every lane (r = 0 makes it a no-op for the owner's column) -- no per-entry selects.
     bool ok = true;
-    double pprod = 1.0, scale = 1.0;
+    double pprod = 1.0;
+    double scale[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) scale[q] = 1.0;
 #pragma unroll
     for (int k = 0; k < MF; ++k) {
-      const double pk = __shfl_sync(hmask, m[k], k, 16);
+      const int qk = k / LPR, jk = k % LPR;
+      const double pk = __shfl_sync(FULL, m[qk][k], jk, LPR);
       ok = ok && (pk > 0.0);
       if (LL) pprod *= pk;
       const double d = rcp_nr(pk);
-      const double r = (c == k) ? 0.0 : m[k] * d;
+      double rr[CPL];
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) rr[q] = (q == qk && j == jk) ? 0.0 : m[q][k] * d;
 #pragma unroll
       for (int a = 0; a < MF; ++a) {
         if (a == k) continue;
-        const double ca = __shfl_sync(hmask, m[a], k, 16);
-        m[a] = fma(-ca, r, m[a]);
+        const double ca = __shfl_sync(FULL, m[qk][a], jk, LPR);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) m[q][a] = fma(-ca, rr[q], m[q][a]);
       }
-      m[k] = (c == k) ? -1.0 : r;
-      if (c == k) scale = d;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) m[q][k] = (q == qk && j == jk) ? -1.0 : rr[q];
+      if (j == jk) scale[qk] = d;
     }
-    if (!ok && c == 0) set_err(p.scal, 1.0);
-    double mi[MF];   // column c of M_i^-1
+    if (!ok && j == 0) set_err(p.scal, 1.0);
 #pragma unroll
-    for (int a = 0; a < MF; ++a) mi[a] = -scale * m[a];
-    double ez = 0.0;
+    for (int q = 0; q < CPL; ++q)
 #pragma unroll
-    for (int a = 0; a < MF; ++a) ez = fma(mi[a], __shfl_sync(hmask, bc, a, 16), ez);
-
+      for (int a = 0; a < MF; ++a) m[q][a] *= -scale[q];      // now column j + LPR q of M_i^-1
+    // ---- (e) ez = M_i^-1 b ;  A_i = ez ez^T + s2 M_i^-1 ---------------------------------------------------------------
+    double ez[CPL], bown[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) ez[q] = bown[q] = 0.0;
+    {
+      const double2* bp = reinterpret_cast<const double2*>(bsrc + n * MF);
+#pragma unroll
+      for (int h = 0; h < MF / 2; ++h) {
+        const double2 bv = bp[h];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          ez[q] = fma(m[q][2 * h], bv.x, ez[q]);
+          ez[q] = fma(m[q][2 * h + 1], bv.y, ez[q]);
+        }
+        // b[j + LPR q] for the likelihood dot product: element a belongs to this lane when a % LPR == j
+        if (((2 * h) % LPR) == j) bown[(2 * h) / LPR] = bv.x;
+        if (((2 * h + 1) % LPR) == j) bown[(2 * h + 1) / LPR] = bv.y;
+      }
+    }
     if (!LL) {
       double* out = EA + n * EASF;
 #pragma unroll
       for (int a = 0; a < MF; ++a) {
-        const double ea = __shfl_sync(hmask, ez, a, 16);
-        const double v = empty ? 0.0 : fma(ea, ez, s2 * mi[a]);
-        if (valid && a >= c) out[a * (a + 1) / 2 + c] = v;
-      }
-      if (valid) out[NVF + c] = empty ? 0.0 : ez;
-    } else {
-      double dot = bc * ez;
+        const double ea = __shfl_sync(FULL, ez[a / LPR], a % LPR, LPR);
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(hmask, dot, o, 16);
-      if (c == 0 && valid && !empty) {
-        const double cnt = (double)(DD - nmiss);
+        for (int q = 0; q < CPL; ++q) {
+          const int c = j + LPR * q;
+          const double v = empty ? 0.0 : fma(ea, ez[q], s2 * m[q][a]);
+          if (valid && a >= c) out[a * (a + 1) / 2 + c] = v;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CPL; ++q)
+        if (valid) out[NVF + j + LPR * q] = empty ? 0.0 : ez[q];
+    } else {
+      double dot = 0.0;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) dot = fma(bown[q], ez[q], dot);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o, LPR);
+      if (j == 0 && valid && !empty) {
+        const double cntd = (double)(DD - nmiss);
         const double logdetM = log(pprod);
-        llacc += cnt * log2pi + ((cnt - (double)MF) * logs2 + logdetM) + (yy[n] - dot) / s2;
+        llacc += cntd * log2pi + ((cntd - (double)MF) * logs2 + logdetM) + (yy[n] - dot) / s2;
       }
     }
   }
@@ -210,7 +270,7 @@ __global__ void __launch_bounds__(256, 1) masked_miss_dmma_kernel(const double* 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int f0 = ((int)blockIdx.y * 8 + w) * 16;     // this warp's 16 features (2 m-tiles)
-  const bool totals = (blockIdx.y == 0 && w == 0);
+  const bool totals = (blockIdx.y == 0);   // every warp of feature group 0 sums 1/8 of the rows (load balance)
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(n_obs, r0 + rows_per_cta);
   const int64_t ntiles = (r1 > r0) ? (r1 - r0 + KB_TR - 1) / KB_TR : 0;
@@ -251,7 +311,7 @@ __global__ void __launch_bounds__(256, 1) masked_miss_dmma_kernel(const double* 
     const uint32_t* mk = reinterpret_cast<const uint32_t*>(kb_smem + s * STAGE_BYTES + EA_BYTES);
     if (totals) {
       const double* tile = reinterpret_cast<const double*>(kb_smem + s * STAGE_BYTES);
-      for (int r = 0; r < rows; ++r) {
+      for (int r = w; r < rows; r += 8) {
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int e = lane + 32 * k;
@@ -286,11 +346,20 @@ __global__ void __launch_bounds__(256, 1) masked_miss_dmma_kernel(const double* 
     for (int nt = 0; nt < KB_NT; ++nt)
       *reinterpret_cast<double2*>(&out[(int64_t)(f0 + mt * 8 + g) * EASF + nt * 8 + 2 * t]) =
           make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-  if (totals) {
+  if (totals) {  // the 8 per-warp partial totals are combined in fixed order through shared memory
+    __syncthreads();
+    double* red = reinterpret_cast<double*>(kb_smem);
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       const int e = lane + 32 * k;
-      if (e < EASF) out[(int64_t)DD * EASF + e] = tot[k];
+      if (e < EASF) red[w * EASF + e] = tot[k];
+    }
+    __syncthreads();
+    for (int e = tid; e < EASF; e += 256) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sacc += red[q * EASF + e];
+      out[(int64_t)DD * EASF + e] = sacc;
     }
   }
 }
@@ -311,7 +380,7 @@ int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart
 
 template <int DD, bool LL>
 int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid) {
-  const int smem = ((DD + 1) * WP + MF * MF + 8 * 2 * MF * 17) * (int)sizeof(double) + 8 * 2 * DD * (int)sizeof(uint16_t);
+  const int smem = ((DD + 1) * WP + MF * MF + 8 * SOLVE_ROWS * MS_STRIDE) * (int)sizeof(double);
   static bool attr_done[64] = {};
   if (!attr_done[sh.dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute((masked_solve_kernel<DD, LL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -325,7 +394,7 @@ int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid)
 
 // E-step solve (ll = false) or likelihood terms (ll = true; per-CTA sums land in sh.partials[0 .. *grid_out))
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out) {
-  int grid = (int)std::min<int64_t>(2 * sm_count(sh.dev), ceil_div(sh.n, 16));
+  int grid = (int)std::min<int64_t>(SOLVE_MINB * sm_count(sh.dev), ceil_div(sh.n, 8 * SOLVE_ROWS));
   if (grid > sh.nparts) grid = sh.nparts;
   if (grid_out) *grid_out = grid;
   switch (s->D) {
