@@ -36,11 +36,16 @@ constexpr int WP = 18;                   // pitch (doubles) of the W rows in sha
 constexpr int LPR = 8;                          // lanes per observation during the sweeps (4: quad, 8: oct)
 constexpr int CPL = MF / LPR;                   // matrix columns per lane
 constexpr int SOLVE_ROWS = 32 / LPR;            // observations per warp
+constexpr int SOLVE_WARPS = 8;                  // warps per CTA
 constexpr int SOLVE_MINB = (LPR == 8) ? 2 : 1;  // CTAs per SM (register budget: CPL x 16 doubles per lane for the matrix)
+// Issuing DMMA (Gram) and DFMA (sweep) work from one SM at the same time costs throughput (tools/fp64_mix.cu: 37 / 34
+// TFLOP/s alone, 23 TFLOP/s mixed), but separating the phases with CTA barriers (1 CTA of 16 warps) measured slower
+// (1.96 ms vs 1.72 ms per 2^20 observations) than letting two 8-warp CTAs drift: kept off.
+constexpr bool SOLVE_PHASED = false;
 constexpr int MS_STRIDE = MF * 17 + 4;          // doubles per staged matrix; +4 spreads the lane groups over the banks
 
 template <int DD, bool LL>
-__global__ void __launch_bounds__(256, SOLVE_MINB) masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ yy,
+__global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ yy,
                                                              const uint32_t* __restrict__ mbits, int64_t n_obs, Par p,
                                                              double* __restrict__ EA, double* __restrict__ partials) {
   constexpr int WPRT = DD / 32;
@@ -68,8 +73,8 @@ __global__ void __launch_bounds__(256, SOLVE_MINB) masked_solve_kernel(const dou
   constexpr unsigned FULL = 0xffffffffu;
   // The trip count depends on blockIdx only, so the compiler can see that every warp stays converged around the
   // shuffles (a warp whose observations lie past the end recomputes the last one and stores nothing).
-  const int64_t cta0 = (int64_t)blockIdx.x * (8 * SOLVE_ROWS);
-  const int64_t stride = (int64_t)gridDim.x * (8 * SOLVE_ROWS);
+  const int64_t cta0 = (int64_t)blockIdx.x * (SOLVE_WARPS * SOLVE_ROWS);
+  const int64_t stride = (int64_t)gridDim.x * (SOLVE_WARPS * SOLVE_ROWS);
   const int64_t iters = (n_obs > cta0) ? (n_obs - cta0 + stride - 1) / stride : 0;
   double llacc = 0.0;
   const double log2pi = 1.8378770664093453, logs2 = LL ? log(s2) : 0.0;
@@ -107,6 +112,7 @@ __global__ void __launch_bounds__(256, SOLVE_MINB) masked_solve_kernel(const dou
     for (int r = 0; r < SOLVE_ROWS; ++r)
       for (int e = cnt[r] + lane; e < nks * 4; e += 32) lst[r * DD + e] = (uint16_t)DD;   // pad with the zero row of Ws
     __syncwarp();
+    if (SOLVE_PHASED) __syncthreads();
     // ---- (b) K-compacted Gram matrices W_miss^T W_miss on the tensor cores (tiles 00, 01, 11 per observation) ----
     {
       double g00[SOLVE_ROWS][2], g01[SOLVE_ROWS][2], g11[SOLVE_ROWS][2];
@@ -136,6 +142,7 @@ __global__ void __launch_bounds__(256, SOLVE_MINB) masked_solve_kernel(const dou
       }
     }
     __syncwarp();
+    if (SOLVE_PHASED) __syncthreads();
     // ---- (c) quad layout: m[q][a] = M[a][j + 4 q] = C0 - Gram ------------------------------------------------------
     const bool valid = nb + rw < n_obs;
     const int64_t n = valid ? nb + rw : n_obs - 1;
@@ -380,13 +387,13 @@ int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart
 
 template <int DD, bool LL>
 int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid) {
-  const int smem = ((DD + 1) * WP + MF * MF + 8 * SOLVE_ROWS * MS_STRIDE) * (int)sizeof(double);
+  const int smem = ((DD + 1) * WP + MF * MF + SOLVE_WARPS * SOLVE_ROWS * MS_STRIDE) * (int)sizeof(double);
   static bool attr_done[64] = {};
   if (!attr_done[sh.dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute((masked_solve_kernel<DD, LL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done[sh.dev & 63] = true;
   }
-  GP_LAUNCH((masked_solve_kernel<DD, LL>), grid, 256, smem, sh.st, bsrc, yy, sh.mbits, sh.n, sh.par, sh.EA, sh.partials);
+  GP_LAUNCH((masked_solve_kernel<DD, LL>), grid, SOLVE_WARPS * 32, smem, sh.st, bsrc, yy, sh.mbits, sh.n, sh.par, sh.EA, sh.partials);
   return GPLVM_OK;
 }
 
@@ -394,7 +401,7 @@ int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid)
 
 // E-step solve (ll = false) or likelihood terms (ll = true; per-CTA sums land in sh.partials[0 .. *grid_out))
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out) {
-  int grid = (int)std::min<int64_t>(SOLVE_MINB * sm_count(sh.dev), ceil_div(sh.n, 8 * SOLVE_ROWS));
+  int grid = (int)std::min<int64_t>(SOLVE_MINB * sm_count(sh.dev), ceil_div(sh.n, SOLVE_WARPS * SOLVE_ROWS));
   if (grid > sh.nparts) grid = sh.nparts;
   if (grid_out) *grid_out = grid;
   switch (s->D) {
