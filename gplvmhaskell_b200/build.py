@@ -31,18 +31,45 @@ def _stamp(paths):
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(HERE, "..", "include", "gplvm_b200.h"))
     for p in sorted(paths + hdrs):
-        h.update(p.encode())
+        h.update(os.path.basename(p).encode())   # names only: the stamp must survive a move of the checkout (gpurun box)
         with open(p, "rb") as f:
             h.update(f.read())
     return h.hexdigest()
+
+
+class _BuildLock:
+    """Inter-process lock: torchrun starts one process per GPU and every rank may call build_library()."""
+
+    def __enter__(self):
+        import fcntl
+        os.makedirs(OBJ, exist_ok=True)
+        self.f = open(os.path.join(OBJ, ".lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = _sources()
     stamp = _stamp(srcs)
     stamp_file = os.path.join(OBJ, "stamp")
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp
+
+    if not force and fresh():
         return LIB
+    with _BuildLock():
+        if not force and fresh():      # another process built it while we waited
+            return LIB
+        return _build_locked(srcs, stamp, stamp_file, verbose)
+
+
+def _build_locked(srcs, stamp, stamp_file, verbose):
     if not os.path.exists(NVCC):
         if os.path.exists(LIB):
             return LIB  # GPU box without a toolkit: use the prebuilt library that travelled with the snapshot
@@ -63,12 +90,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(stamp_file, "w") as f:
+    os.replace(tmp, LIB)               # atomic: a concurrent dlopen never sees a half-written file
+    with open(stamp_file + ".tmp", "w") as f:
         f.write(stamp)
+    os.replace(stamp_file + ".tmp", stamp_file)
     return LIB
 
 
@@ -82,11 +112,14 @@ def build_cli(force: bool = False) -> str:
     if (not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= os.path.getmtime(CLI_SRC)
             and os.path.getmtime(CLI) >= os.path.getmtime(lib)):
         return CLI
-    cmd = ["g++", "-O2", "-std=c++17", CLI_SRC, "-o", CLI, "-L" + HERE, "-lgplvm_b200", "-Wl,-rpath,$ORIGIN",
-           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("g++ failed for the CLI twin:\n%s\n%s" % (r.stdout, r.stderr))
+    with _BuildLock():
+        tmp = CLI + ".tmp.%d" % os.getpid()
+        cmd = ["g++", "-O2", "-std=c++17", CLI_SRC, "-o", tmp, "-L" + HERE, "-lgplvm_b200", "-Wl,-rpath,$ORIGIN",
+               "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed for the CLI twin:\n%s\n%s" % (r.stdout, r.stderr))
+        os.replace(tmp, CLI)
     return CLI
 
 
