@@ -285,6 +285,12 @@ def main():
     barrier()
     launches = lib.gplvm_kernel_launches() - launches0
     total_ms, _ = sess.last_steps_ms()
+    # nvidia-smi samples every 100 ms; when the timed region is shorter than a few samples keep the SAME load running
+    # (untimed) until the clock record has at least 3 samples under load
+    t_extra = time.perf_counter()
+    while len(sampler.lines) < 3 and time.perf_counter() - t_extra < 2.0:
+        sess.steps(args.steps)
+        sess.sync()
     clocks = sampler.stop()
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps

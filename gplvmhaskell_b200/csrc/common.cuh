@@ -117,6 +117,37 @@ __device__ __forceinline__ double rcp_nr(double x) {
   return y;
 }
 
+// In-place inverse of a symmetric positive definite 16 x 16 matrix held column-per-lane by 16 consecutive lanes
+// (lane c = lane & 15 owns m[a] = M[a][c], full symmetric storage), by 16 symmetric sweeps:
+//   step k (pivot p = M[k][k], d = 1/p):  B[i][l] = M[i][l] - M[i][k] M[k][l] d,  B[i][k] = M[i][k] d,  B[k][k] = -d
+// after all 16 steps the registers hold -M^-1; the function returns +M^-1 in m.  Lane c reads M[k][c] from its own
+// column by symmetry, only column k travels (width-16 shuffles).  Lane k keeps column k unscaled and remembers d
+// (applied at the end), so the update formula is identical in every lane.  pprod = product of the pivots = det M;
+// ok = every pivot positive.  All 32 lanes of the warp must call it (two independent matrices per warp).
+__device__ __forceinline__ void sweep_inverse16(double (&m)[16], int c, bool& ok, double& pprod) {
+  double scale = 1.0;
+  ok = true;
+  pprod = 1.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const double pk = __shfl_sync(0xffffffffu, m[k], k, 16);
+    ok = ok && (pk > 0.0);
+    pprod *= pk;
+    const double d = rcp_nr(pk);
+    const double r = (c == k) ? 0.0 : m[k] * d;
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      if (a == k) continue;
+      const double ca = __shfl_sync(0xffffffffu, m[a], k, 16);
+      m[a] = fma(-ca, r, m[a]);
+    }
+    m[k] = (c == k) ? -1.0 : r;
+    if (c == k) scale = d;
+  }
+#pragma unroll
+  for (int a = 0; a < 16; ++a) m[a] *= -scale;
+}
+
 // Sum over the whole block (any blockDim multiple of 32, <= 1024); result valid in every thread.
 // `red` is a shared array of >= 33 doubles.
 __device__ __forceinline__ double block_sum(double v, double* red) {

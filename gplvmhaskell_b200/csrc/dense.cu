@@ -104,15 +104,25 @@ __global__ void __launch_bounds__(256) stats_gemm_kernel(const double* __restric
   }
 }
 
-// stats[i] = sum_p partials[p][i] in fixed order p = 0..nparts-1 (deterministic)
+// stats[i] = sum_p partials[p][i] by a FIXED two-level tree (deterministic): thread (o, grp) of a 256-thread block sums
+// the partials p = grp, grp + 8, ... of output 32 blockIdx.x + o, then the 8 group sums are added in order.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, double* __restrict__ stats,
                                                               int64_t S, int nparts, const double* __restrict__ scal) {
   if (scal && scal[S_DONE] != 0.0) return;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S) return;
+  __shared__ double part[8][33];
+  const int o = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + o;
   double a = 0.0;
-  for (int p = 0; p < nparts; ++p) a += partials[(int64_t)p * S + i];
-  stats[i] = a;
+  if (i < S)
+    for (int p = grp; p < nparts; p += 8) a += partials[(int64_t)p * S + i];
+  part[grp][o] = a;
+  __syncthreads();
+  if (grp == 0 && i < S) {
+    double t = part[0][o];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) t += part[q][o];
+    stats[i] = t;
+  }
 }
 
 // per-feature moments of the local observations.  mode 0: sum x; 1: sum (x-mean)^2; 3: sum x^2;
@@ -291,6 +301,140 @@ __global__ void __launch_bounds__(256) dense_update_kernel(Par p, const double* 
   dense_prep_block(p, sm);  // parameters for the next E-step (also what the LL pass needs)
 }
 
+// Fast path of the replicated update for MP = 16 (the fused-kernel shape): both 16 x 16 problems are inverted in
+// registers by one half-warp each (sweep_inverse16), every per-feature product is statically unrolled, the new W is
+// kept in shared memory for W^T W.  Follows the reference literally: W' = XEz . inv(Ezz) (PPCA.hs:74); the third term
+// |W' U^T|_F^2 with U = chol(Ezz) (PPCA.hs:75-76,79) equals sum_d w'_d^T Ezz w'_d and is evaluated in that form.
+// Also computes the next E-step's M^-1 = (s2' I + W'^T W')^-1, log det and A = W' M^-1 (dense_prep_block).
+// sm: Ezz 256 | Einv 256 | Mm 256 | Mi 256 | red 40 | Ws D x 16
+__global__ void __launch_bounds__(256, 1) dense_update16_kernel(Par p, const double* __restrict__ stats) {
+  extern __shared__ double sm[];
+  if (p.scal[S_DONE] != 0.0) return;
+  constexpr int MP = 16;
+  const int D = p.D, tid = threadIdx.x;
+  double* Ezz = sm;
+  double* Einv = sm + 256;
+  double* Mm = sm + 512;
+  double* Mi = sm + 768;
+  double* red = sm + 1024;
+  double* Ws = sm + 1024 + 40;
+  __shared__ int okflag;
+  const double* XEz = stats;
+  const double* EE = stats + (int64_t)D * MP;
+  const double s2 = p.scal[S_SIGMA2];
+  const double Nd = (double)p.N;
+  Ezz[tid] = Nd * s2 * p.Minv[tid] + EE[tid];
+  if (tid == 0) okflag = 1;
+  __syncthreads();
+  if (tid < 32) {   // lanes 0-15 invert Ezz (lanes 16-31 run the same code on the same matrix: full-warp shuffles)
+    const int c = tid & 15;
+    double m[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) m[a] = Ezz[a * 16 + c];
+    bool ok;
+    double det;
+    sweep_inverse16(m, c, ok, det);
+    if (tid < 16) {
+#pragma unroll
+      for (int a = 0; a < 16; ++a) Einv[a * 16 + c] = m[a];
+      if (!ok && c == 0) okflag = 0;
+    }
+  }
+  __syncthreads();
+  double second = 0.0, third = 0.0, maxdw = 0.0;
+  // volatile views: keep the 16 x 16 operands in shared memory (the compiler would otherwise hoist all 512 loads out
+  // of the feature loop and spill them)
+  const volatile double* Ev = Einv;
+  const volatile double* Zv = Ezz;
+  const volatile double* Miv = Mi;
+  for (int d = tid; d < D; d += 256) {
+    double b[16], x[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) b[a] = XEz[(int64_t)d * MP + a];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t = fma(b[k], Ev[k * 16 + a], t);   // row vector times inv(Ezz)
+      x[a] = t;
+    }
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t = fma(Zv[a * 16 + k], x[k], t);
+      third = fma(x[a], t, third);
+      second = fma(x[a], b[a], second);
+      maxdw = fmax(maxdw, fabs(p.W[(int64_t)d * MP + a] - x[a]));
+    }
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      p.W[(int64_t)d * MP + a] = x[a];
+      Ws[d * 16 + a] = x[a];
+    }
+  }
+  second = 2.0 * block_sum(second, red);
+  third = block_sum(third, red);
+  maxdw = block_max(maxdw, red);
+  __syncthreads();
+  const double news2 = (p.scal[S_TOTAL] - second + third) / (Nd * (double)D);
+  if (tid == 0) {
+    const double dvar = fabs(news2 - s2);
+    p.scal[S_SIGMA2] = news2;
+    p.scal[S_DVAR] = dvar;
+    p.scal[S_MAXDW] = maxdw;
+    p.scal[S_STEPS] += 1.0;
+    if (!okflag || !(news2 > 0.0)) set_err(p.scal, 1.0);
+    if (p.scal[S_USETOL] != 0.0 && !(fmax(dvar, maxdw) > p.scal[S_TOL])) p.scal[S_DONE] = 1.0;
+  }
+  {  // M = s2' I + W'^T W'
+    const int a = tid >> 4, b = tid & 15;
+    double t0 = 0.0, t1 = 0.0;
+    int d = 0;
+    for (; d + 1 < D; d += 2) {
+      t0 = fma(Ws[d * 16 + a], Ws[d * 16 + b], t0);
+      t1 = fma(Ws[(d + 1) * 16 + a], Ws[(d + 1) * 16 + b], t1);
+    }
+    if (d < D) t0 = fma(Ws[d * 16 + a], Ws[d * 16 + b], t0);
+    Mm[tid] = (t0 + t1) + ((a == b) ? news2 : 0.0);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int c = tid & 15;
+    double m[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) m[a] = Mm[a * 16 + c];
+    bool ok;
+    double det;
+    sweep_inverse16(m, c, ok, det);
+    if (tid < 16) {
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+        Mi[a * 16 + c] = m[a];
+        p.Minv[a * 16 + c] = m[a];
+      }
+      if (c == 0) {
+        // log det over the first M pivots only matters when M < 16 (padded columns contribute log s2 each)
+        p.scal[S_LOGDETM] = log(det) - (double)(16 - p.M) * log(news2);
+        if (!ok) set_err(p.scal, 1.0);
+      }
+    }
+  }
+  __syncthreads();
+  for (int d = tid; d < D; d += 256) {
+    double w[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) w[a] = Ws[d * 16 + a];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      double t = 0.0;
+#pragma unroll
+      for (int a = 0; a < 16; ++a) t = fma(w[a], Miv[a * 16 + b], t);
+      p.A[(int64_t)d * MP + b] = t;
+    }
+  }
+}
+
 // LL = -(N/2) (D log 2pi + log det C + tr(C^-1 S)),  S = Xc Xc^T / (N-1)            (PPCA.hs:87-89)
 //   log det C = (D-M) log s2 + log det(s2 I + W^T W);  tr(C^-1 S) = (tr S - tr(Minv W^T S W)) / s2
 // stats (from a statistics pass with A := W): EE = sum_n t_n t_n^T, t_n = W^T xc_n.
@@ -332,7 +476,7 @@ int splits_for(int64_t n_obs, int64_t unit, int tiles_xy) {
 }  // namespace
 
 int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst) {
-  GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 256), 256, 0, sh.st, sh.partials, dst ? dst : sh.stats, S, nparts,
+  GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 32), 256, 0, sh.st, sh.partials, dst ? dst : sh.stats, S, nparts,
             sh.par.scal);
   return GPLVM_OK;
 }
@@ -367,7 +511,7 @@ static int launch_moments(gplvm_ppca_session* s, int mode) {
     const int64_t S = 3 * s->D;
     dim3 grid(ft, ks);
     GP_LAUNCH(moments_kernel, grid, 256, 0, sh.st, sh.X, sh.ldx, sh.n, (int)s->D, mode, sh.par.mu, sh.partials, S, per);
-    GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 256), 256, 0, sh.st, sh.partials, sh.stats, S, ks,
+    GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 32), 256, 0, sh.st, sh.partials, sh.stats, S, ks,
               (const double*)nullptr);
   }
   return GPLVM_OK;
@@ -428,9 +572,20 @@ int dense_enqueue_step(gplvm_ppca_session* s) {
   }
   GP_TRY(session_allreduce_stats(s, s->S));
   const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
+  const bool fast16 = (s->MP == 16 && s->D <= 1024);
+  const size_t smem16 = sizeof(double) * (1024 + 40 + (size_t)s->D * 16);
+  static bool attr_done = false;
+  if (fast16 && !attr_done) {
+    for (ShardState& sh : s->sh) {
+      CUDA_TRY(cudaSetDevice(sh.dev));
+      CUDA_TRY(cudaFuncSetAttribute(dense_update16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
+    }
+    attr_done = true;
+  }
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
-    GP_LAUNCH(dense_update_kernel, 1, 256, smem, sh.st, sh.par, sh.stats);
+    if (fast16) GP_LAUNCH(dense_update16_kernel, 1, 256, smem16, sh.st, sh.par, sh.stats);
+    else GP_LAUNCH(dense_update_kernel, 1, 256, smem, sh.st, sh.par, sh.stats);
   }
   return GPLVM_OK;
 }

@@ -209,7 +209,7 @@ __device__ inline bool block_cholesky_128(double* Ls, double* dinv, int* flag) {
   return *flag != 0;
 }
 
-__global__ void __launch_bounds__(256) gp_diag_kernel(double* __restrict__ A, int64_t ld, int64_t k0, int nb, double* __restrict__ Tinv,
+__global__ void __launch_bounds__(256, 1) gp_diag_kernel(double* __restrict__ A, int64_t ld, int64_t k0, int nb, double* __restrict__ Tinv,
                                                       double* __restrict__ y, double* __restrict__ alpha, double* __restrict__ state) {
   extern __shared__ double sm[];
   double* Ls = sm;
