@@ -1,6 +1,8 @@
 // capi.cu -- one-shot C ABI entry points (host buffers in, host buffers out) built on the session API.
 // They are what the reference's Haskell bodies call: emStepsFast / emStepsMissed of
 // src/GPLVM/PPCA.hs:54-182 and their typed twins in src/GPLVM/TypeSafe/PPCA.hs:91-419.
+#include <thread>
+
 #include "ppca.cuh"
 
 using namespace gplvm;
@@ -42,9 +44,26 @@ int gplvm_ppca(const double* Y, int64_t D, int64_t N, int64_t M, const double* W
   if (!Y || D < 1 || N < 1) return fail(GPLVM_ERR_ARG, "gplvm_ppca: bad input");
   // _noMissedData = not (isNaN (sumAll Y))  (PPCA.hs:44): a NaN anywhere poisons the sum.  The scan is host side
   // because Y is a host buffer at this boundary; it is a flag, not arithmetic.
-  bool has_nan = false;
   const int64_t total = D * N;
-  for (int64_t i = 0; i < total && !has_nan; ++i) has_nan = (Y[i] != Y[i]);
+  std::atomic<bool> found{false};
+  {
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(16, total / (1 << 22)));
+    std::vector<std::thread> pool;
+    const int64_t per = (total + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&, t]() {
+        const int64_t b = t * per, e = std::min<int64_t>(total, b + per);
+        for (int64_t i = b; i < e; i += 4096) {
+          if (found.load(std::memory_order_relaxed)) return;
+          const int64_t ee = std::min<int64_t>(e, i + 4096);
+          bool any = false;
+          for (int64_t q = i; q < ee; ++q) any |= (Y[q] != Y[q]);
+          if (any) { found.store(true); return; }
+        }
+      });
+    for (auto& th : pool) th.join();
+  }
+  const bool has_nan = found.load();
   if (no_missed_out) *no_missed_out = has_nan ? 0 : 1;
   return run_ppca(has_nan, Y, D, N, M, W0, sigma2_0, stop_kind, k, tol, W_out, sigma2_out, loglik_out, restored_out, steps_done);
 }

@@ -131,10 +131,16 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
     for (int b = 0; b < 2; ++b) ee[a][b][0] = ee[a][b][1] = 0.0;
 
   // per-thread address pieces (see the swizzle algebra in DESIGN.md):
-  //   step 1 reads Xc[row 8 nt + g][feature f + t]      -> 16-byte unit (u0 ^ gx), gx = g ^ (t >> 1)
+  //   step 1 reads Xc[row 8 nt + rho1(g)][feature f + t] -> 16-byte unit (u0 ^ gx), gx = rho1(g) ^ (t >> 1)
   //   step 2 reads Xc[row rho(j, t)][feature f8 + g]    -> 16-byte unit (cc ^ pg), pg = (g >> 1) ^ (t << 1)
-  const uint32_t s1_thr = (uint32_t)(g * 128 + (t & 1) * 8);
-  const uint32_t gx4 = (uint32_t)((g ^ (t >> 1)) << 4);
+  // Step-1 n-tiles use the row order rho1(n) = 2 (n & 3) + (n >> 2), i.e. lanes g = 0..3 read rows 0, 2, 4, 6 and
+  // g = 4..7 rows 1, 3, 5, 7 of an 8-row group: a 64-bit shared load is served per half-warp, and rows r, r ^ 1 keep
+  // their two 16-byte units in the same pair of bank groups under SWIZZLE_128B (2-way conflict with rows 0..3).
+  const int rho1g = 2 * (g & 3) + (g >> 2);
+  const uint32_t s1_thr = (uint32_t)(rho1g * 128 + (t & 1) * 8);
+  const uint32_t gx4 = (uint32_t)((rho1g ^ (t >> 1)) << 4);
+  const int rho1c0 = 2 * ((2 * t) & 3) + ((2 * t) >> 2);          // row (within its group of 8) of C-fragment column 2 t
+  const int rho1c1 = 2 * ((2 * t + 1) & 3) + ((2 * t + 1) >> 2);  // ... and of column 2 t + 1
   const uint32_t s2_thr = (uint32_t)(t * 256 + (g & 1) * 8);
   const uint32_t pg4 = (uint32_t)((((g >> 1) ^ (t << 1)) & 7) << 4);
   const uint32_t ez_thr = ez_u + (uint32_t)((t * 2 * EZ_LD + g) * 8);
@@ -195,21 +201,22 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
         dmma(tp[0][1], preg[ks][0], x1);
         dmma(tp[1][1], preg[ks][1], x1);
       }
-      // tp[mt][nt][c] = T[row 8 nt + 2 t + c][latent 8 mt + g]  -> tpart[w][row][latent]
+      // tp[mt][nt][c] = T[row 8 nt + rho1(2 t + c)][latent 8 mt + g]  -> tpart[w][row][latent]
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int c = 0; c < 2; ++c) tpart[(w * RT + nt * 8 + 2 * t + c) * EZ_LD + mt * 8 + g] = tp[mt][nt][c];
+        for (int nt = 0; nt < 2; ++nt) {
+          tpart[(w * RT + nt * 8 + rho1c0) * EZ_LD + mt * 8 + g] = tp[mt][nt][0];
+          tpart[(w * RT + nt * 8 + rho1c1) * EZ_LD + mt * 8 + g] = tp[mt][nt][1];
+        }
       if (MODE == MODE_MASKED_B) {
         yacc0 += __shfl_xor_sync(0xffffffffu, yacc0, 1);
         yacc0 += __shfl_xor_sync(0xffffffffu, yacc0, 2);
         yacc1 += __shfl_xor_sync(0xffffffffu, yacc1, 1);
         yacc1 += __shfl_xor_sync(0xffffffffu, yacc1, 2);
         if (t == 0) {
-          yys[w * RT + g] = yacc0;
-          yys[w * RT + 8 + g] = yacc1;
+          yys[w * RT + rho1g] = yacc0;
+          yys[w * RT + 8 + rho1g] = yacc1;
         }
       }
       __syncthreads();  // S1: partials complete; every warp is also done with step 2 of the previous tile

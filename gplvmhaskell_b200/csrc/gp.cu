@@ -534,6 +534,58 @@ int lookahead_resources(cudaStream_t* sp, cudaEvent_t* e0, cudaEvent_t* e1, cuda
   return GPLVM_OK;
 }
 
+// X (N x R) = L^-1 B on the device, blocked by NB rows: diagonal blocks are inverted in shared memory, the rows
+// below are updated by a CUDA-core kernel (B is overwritten).  L is N x N lower, leading dimension ld.
+int tri_solve_device(const double* dL, int64_t N, int64_t ld, double* dB, int64_t R, double* dX, double* dT, double* dstate,
+                     cudaStream_t st) {
+  for (int64_t k0 = 0; k0 < N; k0 += NB) {
+    const int nb = (int)std::min<int64_t>(NB, N - k0);
+    GP_LAUNCH(tri_inverse_kernel, 1, 256, DIAG_SMEM, st, dL, ld, k0, nb, dT, dstate);
+    GP_LAUNCH(tri_diag_apply_kernel, (unsigned)ceil_div(R, 256), 256, 0, st, dT, nb, dB, dX, R, k0);
+    const int64_t below = N - k0 - nb;
+    if (below > 0) {
+      for (int64_t b0 = 0; b0 < below; b0 += 32768) {
+        dim3 grid((unsigned)ceil_div(R, 256), (unsigned)std::min<int64_t>(32768, below - b0));
+        GP_LAUNCH(tri_update_kernel, grid, 256, 0, st, dL + b0 * ld, ld, N - b0, k0, nb, dX, dB + b0 * R, R);
+      }
+    }
+  }
+  return GPLVM_OK;
+}
+
+// posterior pieces of gpToPosteriorSample (GaussianProcess.hs:80-98)
+// mean[i] = sum_k alpha[k] Lk[k][i]                                                     (:80)
+__global__ void __launch_bounds__(256) gp_post_mean_kernel(const double* __restrict__ alpha, const double* __restrict__ Lk, int64_t nt,
+                                                           int64_t no, double* __restrict__ mean) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= no) return;
+  double s = 0.0;
+  for (int64_t k = 0; k < nt; ++k) s = fma(alpha[k], Lk[k * no + i], s);
+  mean[i] = s;
+}
+// LkT (no x ldt, zero padded columns) = Lk^T ;  C (no x ldc, lower) = K_ss + jitter I                        (:83-85)
+__global__ void __launch_bounds__(256) gp_post_prepare_kernel(const double* __restrict__ Lk, int64_t nt, int64_t no, double* __restrict__ LkT,
+                                                              int64_t ldt, double* __restrict__ Cm, int64_t ldc, KernelSpec ks) {
+  const int64_t i = blockIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ldt) LkT[i * ldt + j] = (j < nt) ? Lk[j * no + i] : 0.0;
+  if (j <= i) {
+    double v = rbf_entry(ks.X + j * ks.Q, ks.X + i * ks.Q, ks.inv_l2, ks.Q, ks.variance);
+    if (i == j) v += ks.jitter;
+    Cm[i * ldc + j] = v;
+  }
+}
+// samples (no x S) = mean 1^T + P normals, P lower (no x ldc)                                                  (:89,95-98)
+__global__ void __launch_bounds__(256) gp_post_sample_kernel(const double* __restrict__ P, int64_t ldc, int64_t no, const double* __restrict__ mean,
+                                                             const double* __restrict__ normals, int64_t S, double* __restrict__ out) {
+  const int64_t i = blockIdx.y;
+  const int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= S) return;
+  double acc = mean[i];
+  for (int64_t k = 0; k <= i; ++k) acc = fma(P[i * ldc + k], normals[k * S + sidx], acc);
+  out[i * S + sidx] = acc;
+}
+
 struct DevBuf {
   void* p = nullptr;
   ~DevBuf() { if (p) cudaFree(p); }
@@ -767,26 +819,96 @@ int gplvm_tri_solve_lower(const double* L, int64_t N, const double* B, int64_t R
   CUDA_TRY(cudaMemsetAsync(dst.p, 0, sizeof(double) * 8, st));
   CUDA_TRY(cudaMemcpyAsync(dL.p, L, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(dB.p, B, sizeof(double) * (size_t)N * R, cudaMemcpyHostToDevice, st));
-  const int diag_smem = DIAG_SMEM;
-  for (int64_t k0 = 0; k0 < N; k0 += NB) {
-    const int nb = (int)std::min<int64_t>(NB, N - k0);
-    GP_LAUNCH(tri_inverse_kernel, 1, 256, diag_smem, st, dL.as<double>(), N, k0, nb, dT.as<double>(), dst.as<double>());
-    GP_LAUNCH(tri_diag_apply_kernel, (unsigned)ceil_div(R, 256), 256, 0, st, dT.as<double>(), nb, dB.as<double>(), dX.as<double>(), R, k0);
-    const int64_t below = N - k0 - nb;
-    if (below > 0) {
-      for (int64_t b0 = 0; b0 < below; b0 += 32768) {
-        dim3 grid((unsigned)ceil_div(R, 256), (unsigned)std::min<int64_t>(32768, below - b0));
-        GP_LAUNCH(tri_update_kernel, grid, 256, 0, st, dL.as<double>() + b0 * N, N, N - b0, k0, nb, dX.as<double>(),
-                  dB.as<double>() + b0 * R, R);
-      }
-    }
-  }
+  GP_TRY(tri_solve_device(dL.as<double>(), N, N, dB.as<double>(), R, dX.as<double>(), dT.as<double>(), dst.as<double>(), st));
   double state[8];
   CUDA_TRY(cudaMemcpyAsync(state, dst.p, sizeof state, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(X_out, dX.p, sizeof(double) * (size_t)N * R, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   if (state[1] != 0.0) return fail(GPLVM_ERR_NUMERIC, "gplvm_tri_solve_lower: singular triangular factor");
+  return GPLVM_OK;
+}
+
+
+int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train, const double* y_train, int64_t n_train, int64_t Q,
+                       const double* inv_lengthscale2, double variance, double jitter_train, double jitter_post,
+                       const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out, double* samples_out) {
+  if (!X_obs || !X_train || !y_train || !inv_lengthscale2 || !mean_out) return fail(GPLVM_ERR_ARG, "gplvm_gp_posterior: null argument");
+  if (n_obs < 1 || n_train < 1 || Q < 1 || Q > 64) return fail(GPLVM_ERR_ARG, "gplvm_gp_posterior: sizes must be positive (Q <= 64)");
+  if (samples_out && (!normals || n_samples < 1)) return fail(GPLVM_ERR_ARG, "gplvm_gp_posterior: normals required for samples");
+  if (n_obs > 32768) return fail(GPLVM_ERR_ARG, "gplvm_gp_posterior: n_obs > 32768 is not supported");
+  GP_TRY(ensure_context());
+  Context& c = ctx();
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  CUDA_TRY(cudaSetDevice(c.shards[0].device));
+  cudaStream_t st = c.shards[0].stream;
+  GP_TRY(set_gemm_attrs());
+  const int64_t ldk = padded_ld(n_train), ldc = padded_ld(n_obs), ldt = round_up(n_train, 4);
+  DevBuf dXo, dXt, dl, dK, dy, dal, dT, dst, dKs, dLk, dLkT, dC, dmean, dnorm, dsamp;
+  CUDA_TRY(cudaMalloc(&dXo.p, sizeof(double) * n_obs * Q));
+  CUDA_TRY(cudaMalloc(&dXt.p, sizeof(double) * n_train * Q));
+  CUDA_TRY(cudaMalloc(&dl.p, sizeof(double) * Q));
+  CUDA_TRY(cudaMalloc(&dK.p, sizeof(double) * (size_t)n_train * ldk));
+  CUDA_TRY(cudaMalloc(&dy.p, sizeof(double) * n_train));
+  CUDA_TRY(cudaMalloc(&dal.p, sizeof(double) * n_train));
+  CUDA_TRY(cudaMalloc(&dT.p, sizeof(double) * NB * NB));
+  CUDA_TRY(cudaMalloc(&dst.p, sizeof(double) * 8));
+  CUDA_TRY(cudaMalloc(&dKs.p, sizeof(double) * (size_t)n_train * n_obs));
+  CUDA_TRY(cudaMalloc(&dLk.p, sizeof(double) * (size_t)n_train * n_obs));
+  CUDA_TRY(cudaMalloc(&dLkT.p, sizeof(double) * (size_t)n_obs * ldt));
+  CUDA_TRY(cudaMalloc(&dC.p, sizeof(double) * (size_t)n_obs * ldc));
+  CUDA_TRY(cudaMalloc(&dmean.p, sizeof(double) * n_obs));
+  CUDA_TRY(cudaMemsetAsync(dst.p, 0, sizeof(double) * 8, st));
+  CUDA_TRY(cudaMemcpyAsync(dXo.p, X_obs, sizeof(double) * n_obs * Q, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dXt.p, X_train, sizeof(double) * n_train * Q, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dl.p, inv_lengthscale2, sizeof(double) * Q, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dy.p, y_train, sizeof(double) * n_train, cudaMemcpyHostToDevice, st));
+  // L = chol(K(train, train) + jitter I), alpha = L^-1 y                                   (GaussianProcess.hs:64-68,77)
+  KernelSpec kt{dXt.as<double>(), dl.as<double>(), variance, jitter_train, (int)Q};
+  GP_TRY(factorise(dK.as<double>(), n_train, ldk, &kt, dy.as<double>(), dal.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  // K_s = k(observe, train): n_train x n_obs (orientation of sqDist, GPExample.hs:83)     (GaussianProcess.hs:71)
+  for (int64_t jj = 0; jj < n_train; jj += 32768) {
+    const int64_t jn = std::min<int64_t>(32768, n_train - jj);
+    dim3 grid((unsigned)ceil_div(n_obs, 512), (unsigned)jn);
+    GP_LAUNCH(rbf_build_kernel, grid, 256, 0, st, dXo.as<double>(), n_obs, dXt.as<double>(), n_train, (int)Q, dl.as<double>(), variance,
+              dKs.as<double>() + jj * n_obs, n_obs, jj, jn);
+  }
+  // Lk = L^-1 K_s                                                                         (GaussianProcess.hs:74)
+  GP_TRY(tri_solve_device(dK.as<double>(), n_train, ldk, dKs.as<double>(), n_obs, dLk.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  GP_LAUNCH(gp_post_mean_kernel, (unsigned)ceil_div(n_obs, 256), 256, 0, st, dal.as<double>(), dLk.as<double>(), n_train, n_obs,
+            dmean.as<double>());
+  CUDA_TRY(cudaMemcpyAsync(mean_out, dmean.p, sizeof(double) * n_obs, cudaMemcpyDeviceToHost, st));
+  if (postfactor_out || samples_out) {
+    // P = chol(K_ss + jitter_post I - Lk^T Lk)                                            (GaussianProcess.hs:83-86)
+    KernelSpec ko{dXo.as<double>(), dl.as<double>(), variance, jitter_post, (int)Q};
+    {
+      dim3 grid((unsigned)ceil_div(std::max(ldt, n_obs), 256), (unsigned)n_obs);
+      GP_LAUNCH(gp_post_prepare_kernel, grid, 256, 0, st, dLk.as<double>(), n_train, n_obs, dLkT.as<double>(), ldt, dC.as<double>(), ldc,
+                ko);
+    }
+    {
+      const int64_t T = ceil_div(n_obs, NB);
+      GP_LAUNCH((gp_gemm_kernel<MODE_SYRK, 64>), (unsigned)(T * (T + 1)), 256, SYRK_SMEM, st, dC.as<double>(), ldc, dLkT.as<double>(), ldt,
+                dLkT.as<double>(), ldt, (int64_t)0, n_obs, (int64_t)0, (int)ldt, nullptr, nullptr, ko, 0);
+    }
+    GP_TRY(factorise(dC.as<double>(), n_obs, ldc, nullptr, nullptr, nullptr, dT.as<double>(), dst.as<double>() + 4, st));
+    if (postfactor_out) GP_TRY(copy_lower_to_host(dC.as<double>(), n_obs, ldc, postfactor_out, st));
+    if (samples_out) {
+      CUDA_TRY(cudaMalloc(&dnorm.p, sizeof(double) * (size_t)n_obs * n_samples));
+      CUDA_TRY(cudaMalloc(&dsamp.p, sizeof(double) * (size_t)n_obs * n_samples));
+      CUDA_TRY(cudaMemcpyAsync(dnorm.p, normals, sizeof(double) * (size_t)n_obs * n_samples, cudaMemcpyHostToDevice, st));
+      dim3 grid((unsigned)ceil_div(n_samples, 256), (unsigned)n_obs);
+      GP_LAUNCH(gp_post_sample_kernel, grid, 256, 0, st, dC.as<double>(), ldc, n_obs, dmean.as<double>(), dnorm.as<double>(), n_samples,
+                dsamp.as<double>());
+      CUDA_TRY(cudaMemcpyAsync(samples_out, dsamp.p, sizeof(double) * (size_t)n_obs * n_samples, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  double state[8];
+  CUDA_TRY(cudaMemcpyAsync(state, dst.p, sizeof state, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (state[1] != 0.0 || state[5] != 0.0)
+    return fail(GPLVM_ERR_NUMERIC, "gplvm_gp_posterior: matrix not positive definite (the reference's cholSH throws; Maybe result Nothing)");
   return GPLVM_OK;
 }
 

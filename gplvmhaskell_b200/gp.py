@@ -72,3 +72,32 @@ def tri_solve_lower(L, B) -> np.ndarray:
     X = np.empty_like(B2)
     _lib.check(lib.gplvm_tri_solve_lower(_lib.dptr(L), L.shape[0], _lib.dptr(B2), B2.shape[1], _lib.dptr(X)))
     return X.reshape(np.asarray(B).shape)
+
+
+def gp_to_posterior_sample(observe, x_train, y_train, normals=None, inv_lengthscale2=(1.0 / 0.1,), variance: float = 1.0,
+                           jitter_train: float = 0.00005, jitter_post: float = 1.0e-6):
+    """gpToPosteriorSample (GaussianProcess.hs:51-98) with caller-supplied standard normals (n_obs x n_samples; the
+    reference draws them from mkStdGen (-4)).  Returns (mean, posterior_factor, samples or None); raises GplvmError
+    where the reference returns Nothing / cholSH throws."""
+    lib = _lib.load()
+    Xo = np.ascontiguousarray(np.asarray(observe, dtype=np.float64).reshape(len(observe), -1))
+    Xt = np.ascontiguousarray(np.asarray(x_train, dtype=np.float64).reshape(len(x_train), -1))
+    yt = np.ascontiguousarray(np.asarray(y_train, dtype=np.float64).reshape(-1))
+    il2 = np.ascontiguousarray(np.asarray(inv_lengthscale2, dtype=np.float64).reshape(-1))
+    no, nt, q = Xo.shape[0], Xt.shape[0], Xo.shape[1]
+    mean = np.empty(no)
+    post = np.empty((no, no))
+    samples = None
+    nrm = None
+    ns = 0
+    if normals is not None:
+        nrm = np.ascontiguousarray(np.asarray(normals, dtype=np.float64).reshape(no, -1))
+        ns = nrm.shape[1]
+        samples = np.empty((no, ns))
+    _lib.check(lib.gplvm_gp_posterior(_lib.dptr(Xo), no, _lib.dptr(Xt), _lib.dptr(yt), nt, q, _lib.dptr(il2), float(variance),
+                                      float(jitter_train), float(jitter_post), _lib.dptr(nrm), ns, _lib.dptr(mean), _lib.dptr(post),
+                                      _lib.dptr(samples)))
+    return mean, post, samples
+
+
+gpToPosteriorSample = gp_to_posterior_sample

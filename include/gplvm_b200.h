@@ -102,6 +102,19 @@ int gplvm_cholesky(const double* A, int64_t N, double* L_out);
  * GaussianProcess.hs:74,77 with the factor taken as lower).  L: N x N, B: N x R row-major, X_out: N x R. */
 int gplvm_tri_solve_lower(const double* L, int64_t N, const double* B, int64_t R, double* X_out);
 
+/* gpToPosteriorSample, src/GPLVM/GaussianProcess.hs:51-98, with the random coefficients supplied by the caller (the
+ * reference draws them from mkStdGen (-4), :95-98) and both Cholesky factors taken as lower:
+ *   K = k(train, train) + jitter_train I (5e-5 in the reference, :67-68), L = chol K;  K_s = k(observe, train)
+ *   (n_train x n_obs, :71);  Lk = L^-1 K_s (:74);  Ly = L^-1 y (:77);  mean = Ly^T Lk (:80);
+ *   P = chol(k(observe, observe) + jitter_post I - Lk^T Lk) (1e-6 in the reference, :83-86);
+ *   samples (n_obs x n_samples) = mean 1^T + P normals (normals: n_obs x n_samples row-major, :89,95-98).
+ * postfactor_out (n_obs x n_obs, lower) and samples_out may be NULL.  GPLVM_ERR_NUMERIC where the reference's Maybe is
+ * Nothing / cholSH throws. */
+int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train, const double* y_train, int64_t n_train,
+                       int64_t Q, const double* inv_lengthscale2, double variance, double jitter_train, double jitter_post,
+                       const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out,
+                       double* samples_out);
+
 /* ---- session API: observation shards resident in HBM ---------------------------------------
  * Used by the one-shot calls above, by bench.py (inputs already resident when the timed region
  * starts) and by multi-process launches (one process per GPU).  A session holds this process's

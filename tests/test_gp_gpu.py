@@ -95,3 +95,26 @@ def test_lml_large_property():
     assert np.max(np.abs(L[rows] @ L.T - Kr)) < 1e-11
     sign, ld = np.linalg.slogdet(ogp.ard_kernel(X, X, il2, 1.0) + 5e-5 * np.eye(n))
     assert abs(logdet - ld) < 1e-8 * abs(ld)
+
+
+def test_posterior_reference_example(gp_golden):
+    """gpToPosteriorSample on the reference's example (GPExample.hs:14-118): 50 test points, 5 training points."""
+    gd = gp_golden
+    rng = np.random.default_rng(4)
+    normals = rng.standard_normal((50, 3))
+    mean, post, samples = g.gp_to_posterior_sample(gd["x_test"], gd["x_train"], gd["y_train"], normals)
+    assert np.max(np.abs(mean - gd["mean"])) < 1e-9
+    # the posterior covariance is numerically rank deficient (1e-6 jitter): compare P P^T, not P
+    assert np.max(np.abs(post @ post.T - gd["post"] @ gd["post"].T)) < 1e-9
+    assert np.max(np.abs(samples - (mean[:, None] + post @ normals))) < 1e-12
+
+
+def test_posterior_vs_oracle_larger():
+    rng = np.random.default_rng(9)
+    xt = np.sort(rng.uniform(-6, 6, 300))
+    yt = np.sin(xt) + 0.05 * rng.standard_normal(300)
+    xo = np.linspace(-5, 5, 411)
+    mean_r, post_r = ogp.gp_posterior_pieces(xo, xt, yt)
+    mean, post, _ = g.gp_to_posterior_sample(xo, xt, yt)
+    assert np.max(np.abs(mean - mean_r)) < 1e-6          # K + 5e-5 I has condition number ~1e7
+    assert np.max(np.abs(post @ post.T - post_r @ post_r.T)) < 1e-6

@@ -87,7 +87,8 @@ def test_dense_left_negative_runs_one_step(iris):
     assert rel(r._W, iris["dense_s1_k0_W"]) < TOL_STEP
 
 
-@pytest.mark.parametrize("d,n,m", [(256, 4096, 16), (256, 1000, 16), (64, 777, 5), (7, 50, 2), (256, 2048, 3), (33, 400, 32)])
+@pytest.mark.parametrize("d,n,m", [(256, 4096, 16), (256, 1000, 16), (64, 777, 5), (7, 50, 2), (256, 2048, 3), (33, 400, 32),
+                                   (128, 3001, 16), (256, 33, 16), (600, 300, 12)])
 def test_dense_steps_vs_oracle_synthetic(d, n, m):
     """The bench shape (D=256, M=16: fused TMA + DMMA kernel), ragged N, and generic shapes."""
     Y, W0 = synth(d, n, m, seed=d * 1000 + n + m)
@@ -196,7 +197,8 @@ def test_missing_tolerance_rule(iris):
 
 
 @pytest.mark.parametrize("d,n,m,p", [(256, 2048, 16, 0.2), (256, 515, 16, 0.5), (40, 300, 5, 0.3), (9, 64, 2, 0.1),
-                                     (256, 1024, 16, 0.0), (48, 200, 32, 0.2)])
+                                     (256, 1024, 16, 0.0), (48, 200, 32, 0.2), (128, 701, 16, 0.3), (64, 333, 16, 0.2),
+                                     (256, 40, 16, 0.2), (256, 97, 16, 0.6)])
 def test_missing_steps_vs_oracle_synthetic(d, n, m, p):
     Y, W0 = synth(d, n, m, seed=7 * d + n, nan_prob=p)
     for k in (0, 3):
