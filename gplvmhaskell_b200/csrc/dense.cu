@@ -574,16 +574,13 @@ int dense_enqueue_step(gplvm_ppca_session* s) {
   const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
   const bool fast16 = (s->MP == 16 && s->D <= 1024);
   const size_t smem16 = sizeof(double) * (1024 + 40 + (size_t)s->D * 16);
-  static bool attr_done = false;
-  if (fast16 && !attr_done) {
-    for (ShardState& sh : s->sh) {
-      CUDA_TRY(cudaSetDevice(sh.dev));
-      CUDA_TRY(cudaFuncSetAttribute(dense_update16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
-    }
-    attr_done = true;
-  }
+  static bool attr_done[64] = {};
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
+    if (fast16 && !attr_done[sh.dev & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(dense_update16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
+      attr_done[sh.dev & 63] = true;
+    }
     if (fast16) GP_LAUNCH(dense_update16_kernel, 1, 256, smem16, sh.st, sh.par, sh.stats);
     else GP_LAUNCH(dense_update_kernel, 1, 256, smem, sh.st, sh.par, sh.stats);
   }

@@ -593,7 +593,10 @@ struct DevBuf {
 };
 
 int set_gemm_attrs() {
-  static bool done = false;
+  static bool done_dev[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  bool& done = done_dev[dev & 63];
   if (done) return GPLVM_OK;
   CUDA_TRY(cudaFuncSetAttribute((gp_gemm_kernel<MODE_PANEL, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute((gp_gemm_kernel<MODE_SYRK, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));

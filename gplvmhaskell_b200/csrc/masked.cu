@@ -598,15 +598,11 @@ static int launch_miss_sums(gplvm_ppca_session* s, ShardState& sh) {
   const int64_t rows_per_cta = round_up(std::max<int64_t>(ceil_div(sh.n, rb), 4), 4);  // 16-byte aligned tile starts
   rb = (int)ceil_div(sh.n, rows_per_cta);
   const int smem = MS_STAGES * (((tr * eas * 8 + 15) & ~15) + ((tr * s->WPR * 4 + 15) & ~15)) + 64;
-  static bool attr_done = false;
-  if (!attr_done) {
-    for (ShardState& t : s->sh) {
-      CUDA_TRY(cudaSetDevice(t.dev));
-      CUDA_TRY(cudaFuncSetAttribute((masked_miss_sums_kernel<5, 8, 16, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute((masked_miss_sums_kernel<18, 2, 8, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    }
-    CUDA_TRY(cudaSetDevice(sh.dev));
-    attr_done = true;
+  static bool attr_done[64] = {};
+  if (!attr_done[sh.dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute((masked_miss_sums_kernel<5, 8, 16, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute((masked_miss_sums_kernel<18, 2, 8, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done[sh.dev & 63] = true;
   }
   if (smem > 200 * 1024) return fail(GPLVM_ERR_ARG, "missing-data PPCA: M too large for the statistics kernel");
   dim3 grid(rb, fgroups);
