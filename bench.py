@@ -132,6 +132,25 @@ def cpu_port_rate(steps: int, warmup: int, sample: int = CPU_SAMPLE):
     return rate_full, dt
 
 
+def cpu_port_rate_missing(steps: int, sample: int = 1 << 13):
+    """Oracle masked EM step (sufficient-statistics restatement of PPCA.hs:106-147, validated against the literal
+    per-observation closures in tests/test_oracle.py) on a bounded sample; returns (it/s at N_FULL, s/step)."""
+    import numpy as np
+    from oracle import ppca as oppca
+    rng = np.random.default_rng(SEED)
+    Y = rng.standard_normal((D, M)) @ rng.standard_normal((M, sample)) + rng.standard_normal((D, 1)) + rng.standard_normal((D, sample))
+    mask = rng.random((D, sample)) < 0.2
+    mask[0] = False
+    Yn = np.where(mask, np.nan, Y)
+    W = np.random.default_rng(4321).standard_normal((D, M))
+    mu, s2 = np.zeros(D), 1.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mu, W, s2, _, _, _ = oppca.missed_step_vectorised(Yn, mu, W, s2)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return (1.0 / dt) * sample / N_FULL, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -371,7 +390,13 @@ def main():
         sess.close()
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and missing:
+        rate, dt_step = cpu_port_rate_missing(steps=8)
+        cpu_baseline = {"value": rate, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": "oracle/ppca.py missed_step_vectorised (NumPy restatement of PPCA.hs:106-147 in sufficient-"
+                                  "statistics form; the literal closures are O(N D) inversions), 8 steps on 2^13 of the 2^23 "
+                                  "observations (%.2f s/step), scaled linearly to 2^23" % dt_step}
+    elif rank == 0 and world == 1 and not args.no_cpu:
         rate, dt_step = cpu_port_rate(steps=12, warmup=1)
         cpu_baseline = {"value": rate, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
                         "sample": "oracle/ppca.py dense_step (NumPy/OpenBLAS restatement of PPCA.hs:63-82, literal op order), "
