@@ -280,3 +280,69 @@ def test_two_gpus_match_one_gpu():
         _lib.check(lib.gplvm_set_devices(1))
     assert rel(res[1][0], res[0][0]) < 1e-11 and abs(res[1][1] - res[0][1]) < 1e-12 * res[0][1]
     assert rel(res[1][3], res[0][3]) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------
+# session API contract (include/gplvm_b200.h)
+# ---------------------------------------------------------------------------------------------------
+
+def test_session_state_and_argument_errors():
+    with pytest.raises(g.GplvmError) as ei:
+        g.Session(8, 100, 40, missing=False)            # M > GPLVM_MAX_M
+    assert ei.value.code == _lib.ERR_ARG
+    with g.Session(8, 100, 3, missing=False) as s:
+        with pytest.raises(g.GplvmError) as ei:
+            s.init(np.zeros((8, 3)), 1.0)                 # no data yet
+        assert ei.value.code == _lib.ERR_STATE
+        s.synth(1)
+        with pytest.raises(g.GplvmError) as ei:
+            s.steps(1)                                    # not initialised
+        assert ei.value.code == _lib.ERR_STATE
+        with pytest.raises(g.GplvmError) as ei:
+            s.init(np.ones((8, 3)), 0.0)                  # sigma2_0 must be positive
+        assert ei.value.code == _lib.ERR_ARG
+        s.init(np.ones((8, 3)) + np.arange(3), 1.0)
+        s.steps(2)
+        with pytest.raises(g.GplvmError) as ei:
+            s.restored()                                  # dense sessions have no restored matrix (Nothing)
+        assert ei.value.code == _lib.ERR_STATE
+        assert s.params()["steps"] == 2
+    with g.Session(8, 100, 3, missing=True) as s:
+        with pytest.raises(g.GplvmError) as ei:
+            s.synth(1, 0.0)
+            s.init(np.ones((8, 3)), 1.0)
+            s.restored()                                  # no EM step executed yet
+        assert ei.value.code == _lib.ERR_STATE
+
+
+def test_session_strided_load_and_read_back():
+    """load_host takes a view into a larger D x ld host matrix; read_data returns the observations (a dense session
+    keeps them centred in HBM and un-centres on the way out: equal up to one rounding)."""
+    rng = np.random.default_rng(5)
+    D, ld, n0, n = 64, 500, 123, 257
+    big = rng.standard_normal((D, ld)) * 3 + 10
+    W0 = rng.standard_normal((D, 4))
+    with g.Session(D, n, 4, missing=False) as s:
+        lib = s.lib
+        view = big[:, n0:]
+        _lib.check(lib.gplvm_session_load_host(s.h, view.ctypes.data_as(_lib._c_double_p), ld))
+        s.init(W0, 1.0)
+        s.steps(3)
+        back = s.read_data()
+        p = s.params()
+    assert np.max(np.abs(back - big[:, n0:n0 + n])) < 1e-13
+    ref = oppca.em_steps_fast(big[:, n0:n0 + n], W0, 1.0, ("left", 2))
+    assert rel(p["W"], ref.W) < 1e-10 and abs(p["sigma2"] - ref.variance) < 1e-10 * ref.variance
+
+
+def test_reinit_restarts_from_new_parameters():
+    Y, W0 = synth(256, 3000, 16, seed=77)
+    with g.Session(256, 3000, 16, missing=False) as s:
+        s.load_host(Y)
+        s.init(W0, 1.0)
+        s.steps(4)
+        a = s.params()
+        s.init(W0, 1.0)          # data already centred: must not be centred twice
+        s.steps(4)
+        b = s.params()
+    assert np.array_equal(a["W"], b["W"]) and a["sigma2"] == b["sigma2"] and b["steps"] == 4
