@@ -8,8 +8,9 @@
 A "step" is one EM iteration over the whole observation matrix (E-step statistics, all-reduce, M-step).
 Workload at every N: synthetic dense PPCA, N_obs = 2^23, D = 256, M = 16, FP64 (BASELINE.json config
 "N=8M, D=256, M=16"), generated on the device by the library's counter-based generator (SURVEY.md 8d);
-with N > 1 GPUs the SAME 2^23 observations are row-sharded over the ranks (strong scaling) and one packed
-NCCL all-reduce per step combines the partial statistics.
+with N > 1 GPUs the SAME 2^23 observations are row-sharded over the ranks (strong scaling); the partial statistics
+(35 KB dense) are combined once per step, by an all-reduce fused into the library's reduction kernel over NVLink peer
+memory (dense) or one packed ncclAllReduce (masked).
 
 value   : EM iterations/s with the observations resident in HBM; device time of exactly K steps (CUDA events
           on the library's stream), max over ranks, after W warm-up steps.  Inputs (17.2 GB at N=1) are far
@@ -292,6 +293,9 @@ def main():
     sess = g.Session(D, n_obs, M, missing=missing, obs_begin=begin, obs_count=count)
     sess.synth(SEED, 0.2 if missing else 0.0)
     sess.init(W0, 1.0)
+    collective = {0: "none (1 GPU)", 1: "one packed ncclAllReduce per step",
+                  2: "all-reduce fused into the reduction kernel over NVLink peer memory (no NCCL call per step)"}.get(
+        lib.gplvm_session_collective(sess.h), "?")
     sess.steps(args.warmup)
     sess.sync()
     barrier()
@@ -408,7 +412,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%s PPCA EM N=%d D=%d M=%d FP64%s" % (args.workload, n_obs, D, M,
                                                                               " 20% NaN" if missing else ""),
-                           "sharding": "observations row-sharded over %d rank(s), one packed NCCL all-reduce per step" % world,
+                           "sharding": "observations row-sharded over %d rank(s)" % world, "collective": collective,
                            "l2": "inputs (%.1f GB per rank) exceed the 126 MB L2; no flush" % (8 * D * count / 1e9),
                            "init": "W0 ~ N(0,1) seed 4321, sigma2_0 = 1"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

@@ -67,6 +67,7 @@ SIGNATURES = {
                                        _c_i64_p]),
     "gplvm_session_loglik": (C.c_int, [C.c_void_p, _c_double_p]),
     "gplvm_session_restored": (C.c_int, [C.c_void_p, _c_double_p, C.c_int64]),
+    "gplvm_session_collective": (C.c_int, [C.c_void_p]),
     "gplvm_session_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "gplvm_session_last_steps_ms": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
     "gplvm_kernel_launches": (C.c_int64, []),

@@ -73,6 +73,8 @@ int shutdown_context();
 // world == 1: no-op.  Enqueued on the shard streams (no host sync).
 int allreduce_sum(const std::vector<double*>& bufs, size_t count);
 
+// recv_host[world][bytes] <- every process's `send` (multi-process mode only; goes through the NCCL communicator)
+int allgather_bytes(const void* send, void* recv_host, size_t bytes);
 int nccl_unique_id(void* id128);
 int nccl_init_rank(int rank, int world, int device, const void* id128);
 

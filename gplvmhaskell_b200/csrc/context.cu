@@ -45,6 +45,7 @@ typedef int (*fn_CommInitRank)(void**, int, NcclUniqueId, int);
 typedef int (*fn_CommInitAll)(void**, int, const int*);
 typedef int (*fn_CommDestroy)(void*);
 typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_Group)(void);
 typedef const char* (*fn_GetErrorString)(int);
 
@@ -55,6 +56,7 @@ struct NcclApi {
   fn_CommInitAll CommInitAll = nullptr;
   fn_CommDestroy CommDestroy = nullptr;
   fn_AllReduce AllReduce = nullptr;
+  fn_AllGather AllGather = nullptr;
   fn_Group GroupStart = nullptr, GroupEnd = nullptr;
   fn_GetErrorString GetErrorString = nullptr;
 } g_nccl;
@@ -74,7 +76,7 @@ int load_nccl() {
 #define LOAD(sym)                                                                  \
   g_nccl.sym = (decltype(g_nccl.sym))dlsym(h, "nccl" #sym);                        \
   if (!g_nccl.sym) return fail(GPLVM_ERR_NCCL, "libnccl lacks symbol nccl" #sym);
-  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommInitAll) LOAD(CommDestroy) LOAD(AllReduce)
+  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommInitAll) LOAD(CommDestroy) LOAD(AllReduce) LOAD(AllGather)
   LOAD(GroupStart) LOAD(GroupEnd) LOAD(GetErrorString)
 #undef LOAD
   g_nccl.handle = h;
@@ -176,6 +178,28 @@ int shutdown_context() {
   c.multiproc = false;
   c.world = 1;
   c.rank = 0;
+  return GPLVM_OK;
+}
+
+int allgather_bytes(const void* send, void* recv_host, size_t bytes) {
+  Context& c = ctx();
+  if (!c.multiproc || c.world == 1) {
+    memcpy(recv_host, send, bytes);
+    return GPLVM_OK;
+  }
+  Shard& sh = c.shards[0];
+  CUDA_TRY(cudaSetDevice(sh.device));
+  char *dsend = nullptr, *drecv = nullptr;
+  CUDA_TRY(cudaMalloc(&dsend, bytes));
+  CUDA_TRY(cudaMalloc(&drecv, bytes * c.world));
+  CUDA_TRY(cudaMemcpyAsync(dsend, send, bytes, cudaMemcpyHostToDevice, sh.stream));
+  int r = g_nccl.AllGather(dsend, drecv, bytes, 0 /* ncclInt8 / ncclChar */, sh.comm, sh.stream);
+  cudaError_t e = cudaMemcpyAsync(recv_host, drecv, bytes * c.world, cudaMemcpyDeviceToHost, sh.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(sh.stream);
+  cudaFree(dsend);
+  cudaFree(drecv);
+  if (r != 0) return fail(GPLVM_ERR_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+  if (e != cudaSuccess) return fail(GPLVM_ERR_CUDA, "allgather copy failed: %s", cudaGetErrorString(e));
   return GPLVM_OK;
 }
 

@@ -106,8 +106,16 @@ __global__ void __launch_bounds__(256) stats_gemm_kernel(const double* __restric
 
 // stats[i] = sum_p partials[p][i] by a FIXED two-level tree (deterministic): thread (o, grp) of a 256-thread block sums
 // the partials p = grp, grp + 8, ... of output 32 blockIdx.x + o, then the 8 group sums are added in order.
+//
+// With pa.peers != nullptr the kernel is also the ALL-REDUCE of the step -- fused reduction + collective over NVLink peer
+// memory, no NCCL call: a block writes its 32 local sums into this rank's publication buffer, raises its epoch flag
+// (system-scope release), waits (bounded) for the same block's flag of every other rank with system-scope acquire loads,
+// then reads the `world` slices straight from the peers' HBM and adds them in RANK ORDER, so every rank forms the
+// bit-identical total and the replicated update stays replicated.  A block publishes before it waits, so no rank can
+// block another.  Two buffers (step parity) suffice: a rank overwrites buffer k & 1 at step k + 2, after all of its
+// blocks have seen every peer's step k + 1 flags, which a peer raises only after its step-k kernel (and reads) finished.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, double* __restrict__ stats,
-                                                              int64_t S, int nparts, const double* __restrict__ scal) {
+                                                              int64_t S, int nparts, double* __restrict__ scal, PeerArgs pa) {
   if (scal && scal[S_DONE] != 0.0) return;
   __shared__ double part[8][33];
   const int o = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -117,11 +125,40 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
     for (int p = grp; p < nparts; p += 8) a += partials[(int64_t)p * S + i];
   part[grp][o] = a;
   __syncthreads();
+  double t = 0.0;
   if (grp == 0 && i < S) {
-    double t = part[0][o];
+    t = part[0][o];
 #pragma unroll
     for (int q = 1; q < 8; ++q) t += part[q][o];
-    stats[i] = t;
+  }
+  if (pa.peers == nullptr) {
+    if (grp == 0 && i < S) stats[i] = t;
+    return;
+  }
+  double* mine = pa.peers[pa.rank];
+  if (grp == 0 && i < S) mine[(int64_t)pa.parity * S + i] = t;
+  __syncthreads();
+  const int64_t flag_off = 2 * S;  // flags: [parity][block] of uint64, after the two data buffers
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned long long* f = reinterpret_cast<unsigned long long*>(mine + flag_off) + (int64_t)pa.parity * gridDim.x + blockIdx.x;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(pa.epoch) : "memory");
+  }
+  if ((int)threadIdx.x < pa.world && (int)threadIdx.x != pa.rank) {
+    const unsigned long long* f =
+        reinterpret_cast<const unsigned long long*>(pa.peers[threadIdx.x] + flag_off) + (int64_t)pa.parity * gridDim.x + blockIdx.x;
+    unsigned long long v = 0;
+    long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    } while (v < pa.epoch && ++spins < (1ll << 22));
+    if (v < pa.epoch) set_err(scal, 3.0);   // never hang the GPU: give up and flag the step
+  }
+  __syncthreads();
+  if (grp == 0 && i < S) {
+    double acc = 0.0;
+    for (int r = 0; r < pa.world; ++r) acc += (r == pa.rank) ? t : __ldcv(pa.peers[r] + (int64_t)pa.parity * S + i);
+    stats[i] = acc;
   }
 }
 
@@ -476,8 +513,10 @@ int splits_for(int64_t n_obs, int64_t unit, int tiles_xy) {
 }  // namespace
 
 int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst) {
+  PeerArgs pa{nullptr, 1, 0, 0, 0ull, (long long)S};
+  if (!dst && sh.peer_args.peers) pa = sh.peer_args;   // set by the dense step when the peer exchange is active
   GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 32), 256, 0, sh.st, sh.partials, dst ? dst : sh.stats, S, nparts,
-            sh.par.scal);
+            sh.par.scal, pa);
   return GPLVM_OK;
 }
 
@@ -512,7 +551,7 @@ static int launch_moments(gplvm_ppca_session* s, int mode) {
     dim3 grid(ft, ks);
     GP_LAUNCH(moments_kernel, grid, 256, 0, sh.st, sh.X, sh.ldx, sh.n, (int)s->D, mode, sh.par.mu, sh.partials, S, per);
     GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 32), 256, 0, sh.st, sh.partials, sh.stats, S, ks,
-              (const double*)nullptr);
+              (double*)nullptr, (PeerArgs{nullptr, 1, 0, 0, 0ull, (long long)S}));
   }
   return GPLVM_OK;
 }
@@ -564,15 +603,26 @@ static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double*
 }
 
 int dense_enqueue_step(gplvm_ppca_session* s) {
+  const bool p2p_step = s->p2p;
+  if (p2p_step) s->xchg_epoch += 1;
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (sh.evk0) CUDA_TRY(cudaEventRecord(sh.evk0, sh.st));
+    if (p2p_step) {
+      sh.peer_args.peers = sh.peers_dev;
+      sh.peer_args.world = ctx().world;
+      sh.peer_args.rank = ctx().multiproc ? ctx().rank : (int)(&sh - &s->sh[0]);
+      sh.peer_args.parity = (int)(s->xchg_epoch & 1);
+      sh.peer_args.epoch = s->xchg_epoch;
+      sh.peer_args.S = (long long)s->S;
+    }
     GP_TRY(dense_stats_pass(s, sh, sh.par.A));
+    sh.peer_args.peers = nullptr;
     if (sh.evk1) CUDA_TRY(cudaEventRecord(sh.evk1, sh.st));
   }
-  GP_TRY(session_allreduce_stats(s, s->S));
   const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
   const bool fast16 = (s->MP == 16 && s->D <= 1024);
+  if (!s->p2p) GP_TRY(session_allreduce_stats(s, s->S));
   const size_t smem16 = sizeof(double) * (1024 + 40 + (size_t)s->D * 16);
   static bool attr_done[64] = {};
   for (ShardState& sh : s->sh) {
@@ -581,8 +631,11 @@ int dense_enqueue_step(gplvm_ppca_session* s) {
       CUDA_TRY(cudaFuncSetAttribute(dense_update16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
       attr_done[sh.dev & 63] = true;
     }
-    if (fast16) GP_LAUNCH(dense_update16_kernel, 1, 256, smem16, sh.st, sh.par, sh.stats);
-    else GP_LAUNCH(dense_update_kernel, 1, 256, smem, sh.st, sh.par, sh.stats);
+    if (fast16) {
+      GP_LAUNCH(dense_update16_kernel, 1, 256, smem16, sh.st, sh.par, sh.stats);
+    } else {
+      GP_LAUNCH(dense_update_kernel, 1, 256, smem, sh.st, sh.par, sh.stats);
+    }
   }
   return GPLVM_OK;
 }

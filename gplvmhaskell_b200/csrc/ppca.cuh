@@ -45,6 +45,14 @@ __device__ __forceinline__ void set_err(double* scal, double code) {
 }
 #endif
 
+// peer-exchange arguments of the fused all-reduce + update kernel
+struct PeerArgs {
+  double* const* peers;      // device array of `world` peer-mapped buffers, nullptr: statistics are local / already reduced
+  int world, rank, parity;
+  unsigned long long epoch;
+  long long S;
+};
+
 struct ShardState {
   int dev = 0;
   cudaStream_t st = nullptr;
@@ -60,6 +68,12 @@ struct ShardState {
   double* partials = nullptr;  // nparts x S
   double* scratch = nullptr;   // per-feature scratch (masked update), D doubles x 4
   void* tmap = nullptr;        // host copy of the CUtensorMap for X (dense DMMA path)
+  // peer exchange of the per-step statistics over NVLink (dense fast path, world > 1): every rank keeps two
+  // publication buffers (step parity) + flags in its own HBM; the update kernel reads all ranks' buffers directly
+  double* xchg = nullptr;          // 2 x S doubles, then 2 x ceil(S / 32) uint64 epoch flags (per parity, per block)
+  double** peers_dev = nullptr;    // device array [world] of peer-mapped `xchg` pointers (own entry included)
+  std::vector<void*> ipc_opened;   // peer mappings opened with cudaIpcOpenMemHandle (multi-process mode)
+  PeerArgs peer_args{nullptr, 1, 0, 0, 0ull, 0};  // non-null peers: the next reduction is also the all-reduce
   int nparts = 0;
   Par par;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
@@ -77,6 +91,8 @@ struct gplvm_ppca_session {
   bool use_dmma = false;   // dense: fused DMMA kernel eligible
   int64_t S = 0;           // packed statistics length
   int64_t steps = 0;       // steps enqueued so far
+  bool p2p = false;        // statistics are exchanged by the update kernel over peer memory (no NCCL call per step)
+  uint64_t xchg_epoch = 0; // number of exchanges published so far (monotonic; selects the buffer parity)
   std::vector<gplvm::ShardState> sh;
 };
 
@@ -104,6 +120,8 @@ int masked_loglik(gplvm_ppca_session* s, double* ll);
 int masked_restore(gplvm_ppca_session* s, double* restored, int64_t ld);
 // session.cu
 int session_allreduce_stats(gplvm_ppca_session* s, size_t count);
+int session_setup_p2p(gplvm_ppca_session* s);
+void session_release_p2p(gplvm_ppca_session* s);
 int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst = nullptr);
 
 // Generic split-K statistics GEMM shared by dense.cu and masked.cu (defined in dense.cu).

@@ -104,6 +104,94 @@ int session_allreduce_stats(gplvm_ppca_session* s, size_t count) {
   return allreduce_sum(bufs, count);
 }
 
+// Peer exchange of the dense per-step statistics (PeerArgs): every rank allocates a publication buffer and maps
+// everyone else's -- directly (cudaDeviceEnablePeerAccess) when one process drives several GPUs, through CUDA IPC
+// handles gathered over the NCCL communicator when there is one process per GPU.  Any failure leaves p2p = false and the
+// step falls back to ncclAllReduce.  GPLVM_NO_P2P=1 disables it.
+int session_setup_p2p(gplvm_ppca_session* s) {
+  Context& c = ctx();
+  s->p2p = false;
+  const char* env = getenv("GPLVM_NO_P2P");
+  if (c.world < 2 || s->missing || !s->use_dmma || s->MP != 16 || s->D > 1024 || (env && atoi(env) != 0)) return GPLVM_OK;
+  const size_t bytes = sizeof(double) * (2 * (size_t)s->S) + sizeof(uint64_t) * 2 * (size_t)ceil_div(s->S, 32) + 64;
+  for (ShardState& sh : s->sh) {
+    if (cudaSetDevice(sh.dev) != cudaSuccess || cudaMalloc(&sh.xchg, bytes) != cudaSuccess ||
+        cudaMemset(sh.xchg, 0, bytes) != cudaSuccess || cudaMalloc(&sh.peers_dev, sizeof(double*) * c.world) != cudaSuccess) {
+      cudaGetLastError();
+      session_release_p2p(s);
+      return GPLVM_OK;
+    }
+  }
+  std::vector<double*> ptrs(c.world, nullptr);
+  if (!c.multiproc) {
+    for (size_t i = 0; i < s->sh.size(); ++i) {
+      for (size_t j = 0; j < s->sh.size(); ++j) {
+        if (i == j) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, s->sh[i].dev, s->sh[j].dev);
+        if (!can) { session_release_p2p(s); return GPLVM_OK; }
+        cudaSetDevice(s->sh[i].dev);
+        cudaError_t e = cudaDeviceEnablePeerAccess(s->sh[j].dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); session_release_p2p(s); return GPLVM_OK; }
+        cudaGetLastError();
+      }
+    }
+    for (size_t i = 0; i < s->sh.size(); ++i) ptrs[i] = s->sh[i].xchg;
+    for (ShardState& sh : s->sh) {
+      cudaSetDevice(sh.dev);
+      if (cudaMemcpy(sh.peers_dev, ptrs.data(), sizeof(double*) * c.world, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); session_release_p2p(s); return GPLVM_OK;
+      }
+    }
+  } else {
+    ShardState& sh = s->sh[0];
+    cudaSetDevice(sh.dev);
+    struct Slot { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+    Slot mine{};
+    mine.ok = (cudaIpcGetMemHandle(&mine.h, sh.xchg) == cudaSuccess) ? 1 : 0;
+    cudaGetLastError();
+    std::vector<Slot> all(c.world);
+    if (allgather_bytes(&mine, all.data(), sizeof(Slot)) != GPLVM_OK) { session_release_p2p(s); return GPLVM_OK; }
+    bool ok = true;
+    for (int r = 0; r < c.world; ++r) ok = ok && all[r].ok;
+    int opened_all = 1;
+    if (ok) {
+      for (int r = 0; r < c.world; ++r) {
+        if (r == c.rank) { ptrs[r] = sh.xchg; continue; }
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened_all = 0; break; }
+        sh.ipc_opened.push_back(q);
+        ptrs[r] = static_cast<double*>(q);
+      }
+    } else {
+      opened_all = 0;
+    }
+    // every rank must take the same decision: gather the outcome
+    std::vector<int> outcome(c.world, 0);
+    if (allgather_bytes(&opened_all, outcome.data(), sizeof(int)) != GPLVM_OK) { session_release_p2p(s); return GPLVM_OK; }
+    for (int r = 0; r < c.world; ++r) opened_all = opened_all && outcome[r];
+    if (!opened_all || cudaMemcpy(sh.peers_dev, ptrs.data(), sizeof(double*) * c.world, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError(); session_release_p2p(s); return GPLVM_OK;
+    }
+  }
+  s->p2p = true;
+  s->xchg_epoch = 0;
+  return GPLVM_OK;
+}
+
+void session_release_p2p(gplvm_ppca_session* s) {
+  for (ShardState& sh : s->sh) {
+    cudaSetDevice(sh.dev);
+    for (void* q : sh.ipc_opened) cudaIpcCloseMemHandle(q);
+    sh.ipc_opened.clear();
+    if (sh.xchg) cudaFree(sh.xchg);
+    if (sh.peers_dev) cudaFree(sh.peers_dev);
+    sh.xchg = nullptr;
+    sh.peers_dev = nullptr;
+  }
+  s->p2p = false;
+}
+
 static int check_async(gplvm_ppca_session* s, double* scal_out) {
   // synchronise every shard and surface numeric failures
   double scal[S_COUNT];
@@ -113,6 +201,8 @@ static int check_async(gplvm_ppca_session* s, double* scal_out) {
     CUDA_TRY(cudaStreamSynchronize(sh.st));
     if (scal[S_ERR] == 2.0)
       return fail(GPLVM_ERR_UNSUPPORTED, "missing-data PPCA: an observation has every feature missing (unsupported by the reference, Util.hs:81)");
+    if (scal[S_ERR] == 3.0)
+      return fail(GPLVM_ERR_NCCL, "peer statistics exchange timed out (a rank did not publish its statistics)");
     if (scal[S_ERR] != 0.0)
       return fail(GPLVM_ERR_NUMERIC, "PPCA: a matrix that must be positive definite is not (step %lld)", (long long)scal[S_STEPS]);
     if (&sh == &s->sh[0] && scal_out) memcpy(scal_out, scal, sizeof scal);
@@ -216,6 +306,7 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
       return rc;
     }
   }
+  session_setup_p2p(s);
   *out = s;
   return GPLVM_OK;
 }
@@ -228,6 +319,7 @@ int gplvm_session_destroy(gplvm_ppca_session* s) {
     cudaStreamSynchronize(sh.st);
   }
   dense_dmma_release(s);
+  session_release_p2p(s);
   for (ShardState& sh : s->sh) free_shard(sh);
   delete s;
   return GPLVM_OK;
@@ -424,6 +516,12 @@ int gplvm_session_restored(gplvm_ppca_session* s, double* restored, int64_t ld) 
   if (!s->initialised || s->steps < 1) return fail(GPLVM_ERR_STATE, "session_restored: run at least one EM step first");
   std::lock_guard<std::recursive_mutex> lk(ctx().mu);
   return masked_restore(s, restored, ld);
+}
+
+int gplvm_session_collective(gplvm_ppca_session* s) {
+  if (!s) return -1;
+  if (ctx().world < 2) return 0;
+  return s->p2p ? 2 : 1;
 }
 
 int gplvm_session_set_kernel_timing(gplvm_ppca_session* s, int on) {

@@ -181,6 +181,11 @@ int gplvm_session_set_kernel_timing(gplvm_ppca_session* s, int on);
  * kernel_ms (nullable) receives the summed duration of the dominant statistics kernel only. */
 int gplvm_session_last_steps_ms(gplvm_ppca_session* s, double* total_ms, double* kernel_ms);
 
+/* How this session combines the per-step statistics of the ranks: 0 = single GPU (nothing to combine), 1 = one packed
+ * ncclAllReduce per step, 2 = all-reduce fused into the library's reduction kernel over NVLink peer memory (direct peer
+ * access or CUDA IPC mappings; dense fused path; GPLVM_NO_P2P=1 forces 1). */
+int gplvm_session_collective(gplvm_ppca_session* s);
+
 /* Number of kernels this library has launched since load (all sessions, this process). */
 int64_t gplvm_kernel_launches(void);
 
