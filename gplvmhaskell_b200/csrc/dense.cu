@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
     long long spins = 0;
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-    } while (v < pa.epoch && ++spins < (1ll << 22));
-    if (v < pa.epoch) set_err(scal, 3.0);   // never hang the GPU: give up and flag the step
+    } while (v < pa.epoch && ++spins < (1ll << 19) && reinterpret_cast<volatile double*>(scal)[S_ERR] != 3.0);
+    if (v < pa.epoch) set_err(scal, 3.0);   // never hang the GPU: give up (~0.5 s) and flag the step; later waits bail out at once
   }
   __syncthreads();
   if (grp == 0 && i < S) {

@@ -113,7 +113,12 @@ int session_setup_p2p(gplvm_ppca_session* s) {
   s->p2p = false;
   const char* env = getenv("GPLVM_NO_P2P");
   if (c.world < 2 || s->missing || !s->use_dmma || s->MP != 16 || s->D > 1024 || (env && atoi(env) != 0)) return GPLVM_OK;
-  const size_t bytes = sizeof(double) * (2 * (size_t)s->S) + sizeof(uint64_t) * 2 * (size_t)ceil_div(s->S, 32) + 64;
+  // [2 x S doubles | 2 x blocks uint64 flags | magic].  Rounded up to whole 2 MB granules: cudaIpcGetMemHandle names the
+  // underlying ALLOCATION, and a small cudaMalloc may be sub-allocated at a non-zero offset inside one (the mapping a
+  // peer opens would then point somewhere else).  Every mapping is additionally verified with a per-rank magic word.
+  const size_t flag_words = 2 * (size_t)ceil_div(s->S, 32);
+  const size_t magic_off = sizeof(double) * (2 * (size_t)s->S) + sizeof(uint64_t) * flag_words;   // byte offset
+  const size_t bytes = (size_t)round_up((int64_t)(magic_off + 64), (int64_t)2 << 20);
   for (ShardState& sh : s->sh) {
     if (cudaSetDevice(sh.dev) != cudaSuccess || cudaMalloc(&sh.xchg, bytes) != cudaSuccess ||
         cudaMemset(sh.xchg, 0, bytes) != cudaSuccess || cudaMalloc(&sh.peers_dev, sizeof(double*) * c.world) != cudaSuccess) {
@@ -148,7 +153,9 @@ int session_setup_p2p(gplvm_ppca_session* s) {
     cudaSetDevice(sh.dev);
     struct Slot { cudaIpcMemHandle_t h; int ok; int pad[3]; };
     Slot mine{};
-    mine.ok = (cudaIpcGetMemHandle(&mine.h, sh.xchg) == cudaSuccess) ? 1 : 0;
+    const unsigned long long my_magic = 0x5eedULL * 1000003ULL + (unsigned long long)c.rank;
+    const bool wrote = cudaMemcpy(reinterpret_cast<char*>(sh.xchg) + magic_off, &my_magic, sizeof my_magic, cudaMemcpyHostToDevice) == cudaSuccess;
+    mine.ok = (wrote && cudaIpcGetMemHandle(&mine.h, sh.xchg) == cudaSuccess) ? 1 : 0;
     cudaGetLastError();
     std::vector<Slot> all(c.world);
     if (allgather_bytes(&mine, all.data(), sizeof(Slot)) != GPLVM_OK) { session_release_p2p(s); return GPLVM_OK; }
@@ -162,6 +169,13 @@ int session_setup_p2p(gplvm_ppca_session* s) {
         if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened_all = 0; break; }
         sh.ipc_opened.push_back(q);
         ptrs[r] = static_cast<double*>(q);
+        unsigned long long seen = 0;   // the mapping must show rank r's magic word
+        if (cudaMemcpy(&seen, static_cast<char*>(q) + magic_off, sizeof seen, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            seen != 0x5eedULL * 1000003ULL + (unsigned long long)r) {
+          cudaGetLastError();
+          opened_all = 0;
+          break;
+        }
       }
     } else {
       opened_all = 0;
