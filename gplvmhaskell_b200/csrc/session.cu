@@ -333,6 +333,12 @@ int gplvm_session_destroy(gplvm_ppca_session* s) {
     cudaStreamSynchronize(sh.st);
   }
   dense_dmma_release(s);
+  if (s->p2p && ctx().multiproc && ctx().world > 1) {
+    // a peer's last reduction may still be reading this rank's publication buffer: rendezvous before unmapping / freeing
+    int token = 1;
+    std::vector<int> all(ctx().world, 0);
+    allgather_bytes(&token, all.data(), sizeof token);
+  }
   session_release_p2p(s);
   for (ShardState& sh : s->sh) free_shard(sh);
   delete s;
