@@ -373,8 +373,6 @@ int gplvm_session_load_host(gplvm_ppca_session* s, const double* Y, int64_t ld) 
   return GPLVM_OK;
 }
 
-static int read_back(gplvm_ppca_session* s, bool restored, double* Yout, int64_t ld);
-
 int gplvm_session_read_data(gplvm_ppca_session* s, double* Y, int64_t ld) {
   if (!s || !Y) return fail(GPLVM_ERR_ARG, "session_read_data: null argument");
   if (!s->has_data) return fail(GPLVM_ERR_STATE, "session_read_data: no data loaded");
