@@ -8,8 +8,8 @@ legs may import it.
 
 PARITY UNPINNED: the reference ships no tests, no golden vectors and cannot be built here (no GHC,
 see SURVEY.md section 8c), so this oracle is pinned only against (i) the closed-form Tipping & Bishop
-fixed point of dense PPCA (tests/test_oracle.py) and (ii) agreement between its literal and its
-sufficient-statistics formulations.
+fixed point of dense PPCA and scikit-learn's PPCA (tests/test_oracle.py), (ii) agreement between its literal and its
+sufficient-statistics formulations and between the dense and masked fixed points on complete data.
 
 All matrices use the reference layout: ``Y`` is D x N (feature-major: rows are features, columns are
 observations; app/Main.hs:24, src/GPLVM/PPCA.hs:41,60), ``W`` is D x M.

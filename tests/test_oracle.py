@@ -125,3 +125,30 @@ def test_ard_reduces_to_reference_kernel(gp_golden):
     g = gp_golden
     K1 = ogp.ard_kernel(g["x_test"][:, None], g["x_train"][:, None], np.array([1.0 / 0.1]), 1.0)
     assert np.array_equal(K1, g["Ks"])
+
+
+def test_dense_fixed_point_matches_sklearn_ppca(iris):
+    """Third-party known answer: scikit-learn's probabilistic PCA (Tipping & Bishop ML solution from an SVD).  sklearn
+    normalises the covariance by N - 1, the EM of the reference by N (PPCA.hs:80), hence the factor."""
+    sk = pytest.importorskip("sklearn.decomposition")
+    Y = iris["Y"]
+    d, n = Y.shape
+    pca = sk.PCA(n_components=3, svd_solver="full").fit(Y.T)
+    r = oppca.em_steps_fast(Y, iris["W0"], 1.0, ("left", 4000))
+    assert abs(r.variance * n / (n - 1) - pca.noise_variance_) < 1e-7 * pca.noise_variance_
+    P_sk = pca.components_.T @ pca.components_
+    assert np.max(np.abs(oppca.projector(r.W) - P_sk)) < 1e-6
+    # model covariance C = W W^T + sigma2 I against sklearn's get_covariance() (same normalisation caveat)
+    C = (r.W @ r.W.T + r.variance * np.eye(d)) * n / (n - 1)
+    assert np.max(np.abs(C - pca.get_covariance())) < 1e-6
+
+
+def test_masked_em_without_nan_reaches_the_dense_fixed_point(iris):
+    """Property tying the two reference algorithms together: on complete data emStepsMissed (which also estimates
+    the mean) converges to the same maximum-likelihood sigma2 and subspace as emStepsFast."""
+    Y = iris["Y"]
+    a = oppca.em_steps_fast(Y, iris["W0"], 1.0, ("left", 3000))
+    b = oppca.em_steps_missed_vectorised(Y, iris["W0"], 1.0, ("left", 3000))
+    assert abs(a.variance - b.variance) < 1e-7 * a.variance
+    assert np.max(np.abs(oppca.projector(a.W) - oppca.projector(b.W))) < 1e-6
+    assert np.max(np.abs(b.restored_matrix - Y)) < 1.0   # the restored matrix is the rank-3 reconstruction (+ mean)
