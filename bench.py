@@ -340,8 +340,12 @@ def main():
         flop_obs = float(flops_per_obs_dense())
     ach_tf = flop_obs * count / (k_ms * 1e-3) * 1e-12
     ach_gbs = bytes_per_obs() * count / (k_ms * 1e-3) * 1e-9
+    # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r1_dense_dmma_ncu_raw.csv: 17.180 GB
+    # read + 4.4 MB written for 2^23 observations = the algorithmic 2048 B/obs; profiles/r1_masked_kernels_ncu_raw.csv:
+    # 7.59 GB over the four masked kernels for 2^20 observations), scaled to this rank's observation count
+    traffic = (7.59e9 / (1 << 20) if missing else (17.180e9 + 4.4e6) / (1 << 23)) * count
     roofline = {"bound": "tensor", "achieved": ach_tf, "peak": dmma.value, "unit": "TFLOP/s", "frac": ach_tf / dmma.value,
-                "traffic": None, "kernel": ("masked E-step + statistics (TMA/DMMA b pass, register solver, DMMA complement sums, DMMA S2 pass) per rank"
+                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum (profiles/), per launch", "kernel": ("masked E-step + statistics (TMA/DMMA b pass, register solver, DMMA complement sums, DMMA S2 pass) per rank"
                            if missing else "dense statistics pass (X.A, X^T.Ez, Ez^T.Ez) per rank"),
                 "kernel_ms": k_ms, "peak_source": "in-run DMMA.8x8x4 register-chain probe (no FP64 entry in MEASURED_PEAKS.json); "
                 "cublasDgemm 8192^3 measured 35.8 TFLOP/s (profiles/r1_fp64_peaks.log)",
