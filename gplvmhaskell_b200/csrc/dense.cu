@@ -151,8 +151,9 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
     long long spins = 0;
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-    } while (v < pa.epoch && ++spins < (1ll << 19) && reinterpret_cast<volatile double*>(scal)[S_ERR] != 3.0);
-    if (v < pa.epoch) set_err(scal, 3.0);   // never hang the GPU: give up (~0.5 s) and flag the step; later waits bail out at once
+    } while (v < pa.epoch && ++spins < (1ll << 23) && reinterpret_cast<volatile double*>(scal)[S_ERR] != 3.0);
+    if (v < pa.epoch) set_err(scal, 3.0);   // never hang the GPU: give up (after seconds of skew) and flag the session; once the
+                                            // flag is up every later wait bails out at once, so a dead peer costs one timeout in total
   }
   __syncthreads();
   if (grp == 0 && i < S) {
