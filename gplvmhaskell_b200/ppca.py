@@ -147,6 +147,20 @@ def check_ppca_input_matrices_prop(y_shape, w0_shape, desired_dimensions: int) -
         raise ValueError("Input matrix should have at least one column")
 
 
+def with_list_of_indexes(y: int, indexes, f):
+    """withListOfIndexes (TypeSafe/PPCA.hs:81-89): run ``f`` on the index list unless an index exceeds the type-level
+    bound ``y`` (the reference compares with ``<``, so ``y`` itself passes); same error text."""
+    indexes = list(indexes)
+    if not indexes:
+        return f([])
+    if y < max(indexes):
+        raise IndexError("index is out of range")
+    return f(indexes)
+
+
+withListOfIndexes = with_list_of_indexes
+
+
 def make_ppca_type_safe(learning_vectors, desired_dimensions: int, stop_parameter: Stop, gen) -> PPCA:
     """makePPCATypeSafe (TypeSafe/PPCA.hs:42-70): same arithmetic, dimension proofs first."""
     Y = np.asarray(learning_vectors, dtype=np.float64)

@@ -73,3 +73,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_with_list_of_indexes_mirrors_reference():
+    assert g.with_list_of_indexes(4, [], lambda ix: ix) == []
+    assert g.with_list_of_indexes(4, [0, 3, 4], lambda ix: sum(ix)) == 7      # y < maximum is the failure test (PPCA.hs:86)
+    with pytest.raises(IndexError, match="index is out of range"):
+        g.with_list_of_indexes(4, [1, 5], lambda ix: ix)
+
+
+def test_stop_parameter_forms():
+    from gplvmhaskell_b200.ppca import _normalise_stop
+    assert _normalise_stop(g.Left(7)) == ("left", 7) and _normalise_stop(3) == ("left", 3)
+    assert _normalise_stop(g.Right(1e-3)) == ("right", 1e-3) and _normalise_stop(0.5) == ("right", 0.5)
+    with pytest.raises(ValueError):
+        _normalise_stop(("middle", 1))
