@@ -88,3 +88,26 @@ def test_stop_parameter_forms():
     assert _normalise_stop(g.Right(1e-3)) == ("right", 1e-3) and _normalise_stop(0.5) == ("right", 0.5)
     with pytest.raises(ValueError):
         _normalise_stop(("middle", 1))
+
+
+def test_header_is_valid_c99_and_links(tmp_path):
+    """include/gplvm_b200.h is a plain C header (what cgo / JNI / Haskell's FFI would consume) and a C program links
+    against the shared library without any C++ or CUDA on the include path."""
+    import subprocess
+    src = tmp_path / "abi_check.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "gplvm_b200.h"\n'
+        "int main(void) {\n"
+        "  double w0[2] = {1.0, 2.0}, y[4] = {0.0, 1.0, 2.0, 3.0};\n"
+        "  int rc = gplvm_ppca_dense(0, 2, 2, 1, w0, 1.0, GPLVM_STOP_ITERATIONS, 1, 0.0, 0, 0, 0, 0);\n"
+        '  printf("%d %s %s\\n", rc, gplvm_version(), gplvm_last_error());\n'
+        "  (void)y; return rc == GPLVM_ERR_ARG ? 0 : 1;\n}\n")
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(_lib.library_path())
+    g.load_library()
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L" + libdir, "-lgplvm_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sm_100a" in r.stdout and "null" in r.stdout
