@@ -375,6 +375,11 @@ int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj) 
     return e ? (atoi(e) != 0) : false;
   }();
   if (use_ws) return dense_ws_stats(s, sh, proj);
+  static const bool use_v2 = []() {
+    const char* e = getenv("GPLVM_DENSE_V2");
+    return e ? (atoi(e) != 0) : false;
+  }();
+  if (use_v2) return dense_v2_stats(s, sh, proj);
   int grid = 0;
   GP_TRY(dispatch_dmma<MODE_DENSE>(s, sh, proj, s->S, MaskedArgs(), &grid));
   return launch_reduce_partials(sh, s->S, grid);
