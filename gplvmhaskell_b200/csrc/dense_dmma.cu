@@ -368,18 +368,6 @@ int dense_dmma_prepare(gplvm_ppca_session* s) {
 }
 
 int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj) {
-  static const bool use_ws = []() {
-    // experimental warp-specialised variant (dense_ws.cu): correct, but measured 5.25 ms vs 4.72 ms per step at
-    // N = 2^23 (the 128-register budget of 2 x 256-thread CTAs leaves the compiler less room to hoist fragment loads)
-    const char* e = getenv("GPLVM_DENSE_WS");
-    return e ? (atoi(e) != 0) : false;
-  }();
-  if (use_ws) return dense_ws_stats(s, sh, proj);
-  static const bool use_v2 = []() {
-    const char* e = getenv("GPLVM_DENSE_V2");
-    return e ? (atoi(e) != 0) : false;
-  }();
-  if (use_v2) return dense_v2_stats(s, sh, proj);
   int grid = 0;
   GP_TRY(dispatch_dmma<MODE_DENSE>(s, sh, proj, s->S, MaskedArgs(), &grid));
   return launch_reduce_partials(sh, s->S, grid);

@@ -107,8 +107,6 @@ bool dense_dmma_eligible(const gplvm_ppca_session* s);
 int dense_dmma_prepare(gplvm_ppca_session* s);
 int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int dense_dmma_release(gplvm_ppca_session* s);
-int dense_ws_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
-int dense_v2_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int masked_dmma_b(gplvm_ppca_session* s, ShardState& sh, const double* W, const double* mu, double* bout, double* yyout);
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out);
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);

@@ -215,8 +215,6 @@ static int check_async(gplvm_ppca_session* s, double* scal_out) {
     CUDA_TRY(cudaStreamSynchronize(sh.st));
     if (scal[S_ERR] == 2.0)
       return fail(GPLVM_ERR_UNSUPPORTED, "missing-data PPCA: an observation has every feature missing (unsupported by the reference, Util.hs:81)");
-    if (scal[S_ERR] == 4.0)
-      return fail(GPLVM_ERR_CUDA, "dynamic shared memory base is not 1024-byte aligned (dense_v2 kernel)");
     if (scal[S_ERR] == 3.0)
       return fail(GPLVM_ERR_NCCL, "peer statistics exchange timed out (a rank did not publish its statistics)");
     if (scal[S_ERR] != 0.0)
