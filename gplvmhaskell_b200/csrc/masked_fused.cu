@@ -47,7 +47,8 @@ constexpr int MS_STRIDE = MF * 17 + 4;          // doubles per staged matrix; +4
 template <int DD, bool LL>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ yy,
                                                              const uint32_t* __restrict__ mbits, int64_t n_obs, Par p,
-                                                             double* __restrict__ EA, double* __restrict__ partials) {
+                                                             double* __restrict__ EA, double* __restrict__ partials,
+                                                             uint32_t* __restrict__ eamax) {
   constexpr int WPRT = DD / 32;
   static_assert(WPRT <= 8, "mask words per observation");
   if (!LL && p.scal[S_DONE] != 0.0) return;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_ker
   const int64_t stride = (int64_t)gridDim.x * (SOLVE_WARPS * SOLVE_ROWS);
   const int64_t iters = (n_obs > cta0) ? (n_obs - cta0 + stride - 1) / stride : 0;
   double llacc = 0.0;
+  uint32_t mxa = 0u, mxe = 0u;   // high words of the largest |vech A| and |ez| entries written (scale of masked_imma.cu)
   const double log2pi = 1.8378770664093453, logs2 = LL ? log(s2) : 0.0;
 
   for (int64_t it = 0; it < iters; ++it) {
@@ -225,12 +227,19 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_ker
         for (int q = 0; q < CPL; ++q) {
           const int c = j + LPR * q;
           const double v = empty ? 0.0 : fma(ea, ez[q], s2 * m[q][a]);
-          if (valid && a >= c) out[a * (a + 1) / 2 + c] = v;
+          if (valid && a >= c) {
+            out[a * (a + 1) / 2 + c] = v;
+            mxa = max(mxa, (uint32_t)__double2hiint(v) & 0x7fffffffu);
+          }
         }
       }
 #pragma unroll
       for (int q = 0; q < CPL; ++q)
-        if (valid) out[NVF + j + LPR * q] = empty ? 0.0 : ez[q];
+        if (valid) {
+          const double v = empty ? 0.0 : ez[q];
+          out[NVF + j + LPR * q] = v;
+          mxe = max(mxe, (uint32_t)__double2hiint(v) & 0x7fffffffu);
+        }
     } else {
       double dot = 0.0;
 #pragma unroll
@@ -247,6 +256,13 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_ker
   if (LL) {
     const double tsum = block_sum(llacc, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = tsum;
+  } else if (eamax != nullptr) {
+    mxa = __reduce_max_sync(FULL, mxa);
+    mxe = __reduce_max_sync(FULL, mxe);
+    if (lane == 0) {
+      atomicMax(&eamax[0], mxa);   // max is order-independent: deterministic
+      atomicMax(&eamax[1], mxe);
+    }
   }
 }
 
@@ -393,7 +409,9 @@ int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid)
     CUDA_TRY(cudaFuncSetAttribute((masked_solve_kernel<DD, LL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done[sh.dev & 63] = true;
   }
-  GP_LAUNCH((masked_solve_kernel<DD, LL>), grid, SOLVE_WARPS * 32, smem, sh.st, bsrc, yy, sh.mbits, sh.n, sh.par, sh.EA, sh.partials);
+  if (!LL && sh.eamax) CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 2 * sizeof(uint32_t), sh.st));
+  GP_LAUNCH((masked_solve_kernel<DD, LL>), grid, SOLVE_WARPS * 32, smem, sh.st, bsrc, yy, sh.mbits, sh.n, sh.par, sh.EA, sh.partials,
+            LL ? nullptr : sh.eamax);
   return GPLVM_OK;
 }
 
@@ -415,6 +433,12 @@ int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc
 
 // complement sums [G^miss | S1^miss] (D x 152) + totals (152) into dst (length (D + 1) x 152)
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
+  // default: exact fixed-point sums on the INT8 tensor cores (masked_imma.cu); GPLVM_MISS_DMMA=1 keeps the FP64 DMMA product
+  static const bool use_dmma = []() {
+    const char* e = getenv("GPLVM_MISS_DMMA");
+    return e ? (atoi(e) != 0) : false;
+  }();
+  if (!use_dmma && sh.mbitsT) return masked_imma_miss_sums(s, sh, dst);
   const int64_t Spart = (int64_t)(s->D + 1) * EASF;
   const int fgroups = (int)std::max<int64_t>(1, s->D / 128);
   int rb = (int)std::min<int64_t>(std::max<int64_t>(1, sm_count(sh.dev) / fgroups), sh.nparts);

@@ -1,0 +1,332 @@
+// masked_imma.cu -- complement sums of the NaN-masked M-step as an EXACT fixed-point product on the INT8 tensor
+// cores (mma.sync.m16n8k32.s8.u8 -> s32; 1.14 POP/s on B200, tools/imma_peak.cu, against 37 TFLOP/s of DMMA).
+//
+//   miss (D x 152) = Miss^T (D x n) . [vech A | ez] (n x 152),   Miss[i][d] = 1 when observation i misses feature d
+// (reference: the per-feature sums over the observations that miss / have the feature, emStepsMissed.stepTwo,
+// src/GPLVM/PPCA.hs:119-147; complement form).
+//
+// One factor is exactly 0 / 1, so only the other needs splitting: every [vech A | ez] entry v is rounded ONCE to the
+// fixed-point grid of its column class,  x = rint(v 2^(51 - E)),  |v| < 2^E  (E from the largest |entry| of the class --
+// vech A or ez -- which the solver kernel tracks with an integer max), and  u = x + 2^51  in [0, 2^52] is cut into its
+// 7 bytes.  Byte planes are u8 B-operands, the mask bits expand to s8 A-operands, the products accumulate exactly in
+// s32, and a constant-1 column counts the offsets:  sum_i x_i = sum_s 256^s S_s - 2^51 cnt.  All sums are integers =>
+// independent of the summation order and of the split of the observations over CTAs: bitwise reproducible.  The one
+// rounding per entry is <= 2^-52 of the class maximum, i.e. no worse than the rounding of a single FP64 addition of that
+// entry into a running sum; the accumulated sum itself is exact and is rounded to FP64 once at the end.
+//
+// Kernel: CTA = (column group, observation split).  The 152 columns form 8 groups of 10 and 8 groups of 9
+// (10 x 7 + 1 = 71 -> 9 n-tiles, 9 x 7 + 1 = 64 -> 8 n-tiles: < 1 % padding); the groups get 20 / 17 observation splits
+// so that the 296 CTAs (2 per SM) carry equal work.  Per 128-observation chunk: every thread loads 4 or 8 entries, cuts
+// them and stores byte planes to shared memory (k-contiguous, pitch 160 B: conflict-free 64-bit fragment loads);
+// then 4 k32 steps of 2 x NT IMMAs per warp (8 warps x 32 features).  Tiles are double buffered: one barrier per chunk.
+// The totals row (sum over ALL observations) is accumulated by the cutting threads as integer sums of the two halves
+// of u.  A small finalize kernel adds the splits in int64, assembles the 128-bit integers and rounds once.
+#include "ppca.cuh"
+#include "tma.cuh"
+
+namespace gplvm {
+namespace {
+
+constexpr int NSL = 7;              // byte planes of the 52-bit fixed-point value
+constexpr int FXP = 51;             // |x| < 2^FXP
+constexpr int IM_CHUNK = 128;       // observations per shared-memory tile
+constexpr int IM_PITCH = 160;       // bytes per tile row (128 + 32: rows 4 apart in g land in different bank groups)
+constexpr int IM_LDP = 72;          // int32 columns per feature row in the per-CTA partial block
+constexpr int IM_EAS = 152;
+constexpr int IM_NV = 136;
+constexpr int IM_G10 = 8;           // groups 0..7: 10 columns each (0..79); groups 8..15: 9 columns each (80..151)
+
+__device__ __forceinline__ void imma_s8u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 4 mask bits -> 4 bytes of 0 / 1 (bit i lands at position 8 i; the 16 partial products never collide)
+__device__ __forceinline__ uint32_t expand4(uint32_t x) { return ((x & 15u) * 0x00204081u) & 0x01010101u; }
+
+// biased exponent of the class maximum, clamped so that both 2^(51 - E) and 2^(E - 51) are normal numbers
+__device__ __forceinline__ int class_exponent(uint32_t hmax) {
+  int ex = (int)((hmax >> 20) & 0x7ffu);
+  return min(max(ex, 60), 2040);
+}
+__device__ __forceinline__ double scale_up(uint32_t hmax) {      // 2^(FXP - E),  E = ex - 1022
+  return __hiloint2double((1023 + FXP + 1022 - class_exponent(hmax)) << 20, 0);
+}
+__device__ __forceinline__ double scale_down(uint32_t hmax) {    // 2^(E - FXP)
+  return __hiloint2double((1023 - FXP - 1022 + class_exponent(hmax)) << 20, 0);
+}
+
+// cuts 4 consecutive observations of one column into byte planes and stores plane s as one 32-bit word
+__device__ __forceinline__ void cut_store(const double (&v)[4], double sc, int64_t o0, int64_t n_obs, uint32_t dst,
+                                          unsigned long long& tlo, unsigned long long& thi) {
+  uint32_t lo[4], hi[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const double y = fma(v[r], sc, 6755399441055744.0);   // 2^52 + 2^51: the mantissa of y is the integer x + 2^51
+    lo[r] = (uint32_t)__double2loint(y);
+    hi[r] = (uint32_t)__double2hiint(y) - 0x43300000u;
+    if (o0 + r < n_obs) {
+      tlo += lo[r];
+      thi += hi[r];
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NSL; ++s) {
+    const uint32_t sel = (uint32_t)((s & 3) | (((s & 3) + 4) << 4));
+    const uint32_t w01 = (s < 4) ? __byte_perm(lo[0], lo[1], sel) : __byte_perm(hi[0], hi[1], sel);
+    const uint32_t w23 = (s < 4) ? __byte_perm(lo[2], lo[3], sel) : __byte_perm(hi[2], hi[3], sel);
+    const uint32_t wv = __byte_perm(w01, w23, 0x5410u);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + (uint32_t)(s * IM_PITCH)), "r"(wv) : "memory");
+  }
+}
+
+template <int DD, int NC>
+__device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, const uint32_t* __restrict__ mT, int64_t nwT,
+                                               int64_t n_obs, int col0, int64_t chunk_begin, int64_t chunk_end,
+                                               const uint32_t* __restrict__ eamax, int* __restrict__ ipart,
+                                               unsigned long long* __restrict__ tpart, uint8_t* smem) {
+  constexpr int MT = DD / 128;                     // m16 tiles per warp (8 warps cover DD features)
+  constexpr int NT = (NC * NSL + 1 + 7) / 8;       // n8 tiles: NC x 7 byte planes + the count column
+  constexpr int NROW = NT * 8;
+  static_assert(NROW <= IM_LDP, "partial block pitch");
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t* smem32 = reinterpret_cast<uint32_t*>(smem);
+  for (int e = tid; e < 2 * NROW * (IM_PITCH / 4); e += 256) {
+    const int row = (e / (IM_PITCH / 4)) % NROW;
+    smem32[e] = (row == NC * NSL) ? 0x01010101u : 0u;   // count column: all ones; padding columns: zero
+  }
+  __syncthreads();
+  int acc[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0;
+
+  // cutting assignment: lane = group of 4 observations of the chunk, warp = column (warps 0 .. NC - 9 take a second one)
+  const int ca = w, cb = w + 8;
+  const bool has_b = cb < NC;
+  const uint32_t hA = eamax[0], hE = eamax[1];
+  const double sca = scale_up((col0 + ca < IM_NV) ? hA : hE);
+  const double scb = scale_up((col0 + cb < IM_NV) ? hA : hE);
+  unsigned long long tlo[2] = {0ull, 0ull}, thi[2] = {0ull, 0ull};
+  const int kq = lane;
+  // k-word (kq & 7) = 4 h + t' of k32 step (kq >> 3) is stored at word 2 t' + h: (b0, b1) of a fragment are one 64-bit load
+  const uint32_t kpos = (uint32_t)(((kq >> 3) * 8 + 2 * (kq & 3) + ((kq >> 2) & 1)) * 4);
+  const uint32_t smem_u = smem_u32(smem);
+  const uint32_t* mrow[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) mrow[mt][r] = mT + (int64_t)(w * 16 * MT + mt * 16 + g + 8 * r) * nwT;
+
+  for (int64_t chunk = chunk_begin; chunk < chunk_end; ++chunk) {
+    const uint32_t tile_u = smem_u + (uint32_t)(((chunk - chunk_begin) & 1) * NROW * IM_PITCH);
+    uint4 mk[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) mk[mt][r] = __ldg(reinterpret_cast<const uint4*>(mrow[mt][r] + chunk * 4));
+    const int64_t o0 = chunk * IM_CHUNK + 4 * kq;
+    double va[4], vb[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t oi = min(o0 + r, n_obs - 1);
+      va[r] = EA[oi * IM_EAS + col0 + ca];
+      vb[r] = has_b ? EA[oi * IM_EAS + col0 + cb] : 0.0;
+    }
+    cut_store(va, sca, o0, n_obs, tile_u + (uint32_t)(ca * NSL * IM_PITCH) + kpos, tlo[0], thi[0]);
+    if (has_b) cut_store(vb, scb, o0, n_obs, tile_u + (uint32_t)(cb * NSL * IM_PITCH) + kpos, tlo[1], thi[1]);
+    __syncthreads();   // tile complete; every warp finished the MMAs of the previous use of the other buffer
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t w0 = (ks == 0) ? mk[mt][0].x : (ks == 1) ? mk[mt][0].y : (ks == 2) ? mk[mt][0].z : mk[mt][0].w;
+        const uint32_t w1 = (ks == 0) ? mk[mt][1].x : (ks == 1) ? mk[mt][1].y : (ks == 2) ? mk[mt][1].z : mk[mt][1].w;
+        a[mt][0] = expand4(w0 >> (4 * t));
+        a[mt][1] = expand4(w1 >> (4 * t));
+        a[mt][2] = expand4(w0 >> (16 + 4 * t));
+        a[mt][3] = expand4(w1 >> (16 + 4 * t));
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        uint32_t b0, b1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                     : "=r"(b0), "=r"(b1)
+                     : "r"(tile_u + (uint32_t)((nt * 8 + g) * IM_PITCH + ks * 32 + 8 * t)));
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) imma_s8u8(acc[mt][nt], a[mt], b0, b1);
+      }
+    }
+  }
+  // per-CTA exact partial sums
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int f = w * 16 * MT + mt * 16 + g;
+      *reinterpret_cast<int2*>(&ipart[(int64_t)f * IM_LDP + nt * 8 + 2 * t]) = make_int2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<int2*>(&ipart[(int64_t)(f + 8) * IM_LDP + nt * 8 + 2 * t]) = make_int2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tlo[q] += __shfl_xor_sync(0xffffffffu, tlo[q], o);
+      thi[q] += __shfl_xor_sync(0xffffffffu, thi[q], o);
+    }
+  }
+  if (lane == 0) {
+    tpart[ca * 2] = tlo[0];
+    tpart[ca * 2 + 1] = thi[0];
+    if (has_b) {
+      tpart[cb * 2] = tlo[1];
+      tpart[cb * 2 + 1] = thi[1];
+    }
+  }
+}
+
+// CTA index -> (column group, split): groups 0..7 (10 columns) have s10 splits each, groups 8..15 (9 columns) s9
+struct ImmaPlan {
+  int s10, s9;
+};
+__host__ __device__ inline void imma_locate(const ImmaPlan& pl, int cta, int& group, int& split, int& nsplit) {
+  if (cta < IM_G10 * pl.s10) {
+    group = cta / pl.s10;
+    split = cta % pl.s10;
+    nsplit = pl.s10;
+  } else {
+    cta -= IM_G10 * pl.s10;
+    group = IM_G10 + cta / pl.s9;
+    split = cta % pl.s9;
+    nsplit = pl.s9;
+  }
+}
+
+template <int DD>
+__global__ void __launch_bounds__(256, 2) masked_miss_imma_kernel(const double* __restrict__ EA, const uint32_t* __restrict__ mT,
+                                                                 int64_t nwT, int64_t n_obs, ImmaPlan pl,
+                                                                 const uint32_t* __restrict__ eamax, int* __restrict__ ipart,
+                                                                 unsigned long long* __restrict__ tpart,
+                                                                 const double* __restrict__ scal) {
+  if (scal[S_DONE] != 0.0) return;
+  extern __shared__ __align__(16) uint8_t im_smem[];
+  int group, split, nsplit;
+  imma_locate(pl, (int)blockIdx.x, group, split, nsplit);
+  const int64_t nchunks = (n_obs + IM_CHUNK - 1) / IM_CHUNK;
+  const int64_t c0 = nchunks * split / nsplit, c1 = nchunks * (split + 1) / nsplit;
+  int* ip = ipart + (int64_t)blockIdx.x * DD * IM_LDP;
+  unsigned long long* tp = tpart + (int64_t)blockIdx.x * 20;
+  if (group < IM_G10)
+    miss_imma_body<DD, 10>(EA, mT, nwT, n_obs, group * 10, c0, c1, eamax, ip, tp, im_smem);
+  else
+    miss_imma_body<DD, 9>(EA, mT, nwT, n_obs, 80 + (group - IM_G10) * 9, c0, c1, eamax, ip, tp, im_smem);
+}
+
+// dst[f][c] (f < D: complement sums of feature f; f = D: totals over all observations), each rounded to FP64 once
+__global__ void __launch_bounds__(256) masked_miss_imma_finalize(const int* __restrict__ ipart, const unsigned long long* __restrict__ tpart,
+                                                                 int D, ImmaPlan pl, int64_t n_obs, const uint32_t* __restrict__ eamax,
+                                                                 double* __restrict__ dst, const double* __restrict__ scal) {
+  if (scal[S_DONE] != 0.0) return;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (D + 1) * IM_EAS) return;
+  const int f = idx / IM_EAS, c = idx % IM_EAS;
+  const int group = (c < 80) ? c / 10 : IM_G10 + (c - 80) / 9;
+  const int lc = (c < 80) ? c % 10 : (c - 80) % 9;
+  const int nc = (group < IM_G10) ? 10 : 9;
+  const int nsplit = (group < IM_G10) ? pl.s10 : pl.s9;
+  const int cta0 = (group < IM_G10) ? group * pl.s10 : IM_G10 * pl.s10 + (group - IM_G10) * pl.s9;
+  __int128 T = 0;
+  if (f < D) {
+    long long S[NSL], cnt = 0;
+#pragma unroll
+    for (int s = 0; s < NSL; ++s) S[s] = 0;
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const int* base = ipart + ((int64_t)(cta0 + sp) * D + f) * IM_LDP;
+#pragma unroll
+      for (int s = 0; s < NSL; ++s) S[s] += base[lc * NSL + s];
+      cnt += base[nc * NSL];
+    }
+#pragma unroll
+    for (int s = 0; s < NSL; ++s) T += (__int128)S[s] << (8 * s);
+    T -= (__int128)cnt << FXP;
+  } else {
+    unsigned long long lo = 0ull, hi = 0ull;
+    for (int sp = 0; sp < nsplit; ++sp) {
+      lo += tpart[(int64_t)(cta0 + sp) * 20 + lc * 2];
+      hi += tpart[(int64_t)(cta0 + sp) * 20 + lc * 2 + 1];
+    }
+    T = ((__int128)hi << 32) + (__int128)lo - ((__int128)n_obs << FXP);
+  }
+  // |T| < 2^(51 + 24): the upper part is exact in FP64, one fused rounding when the low 24 bits are added
+  const long long thi = (long long)(T >> 24), tlo = (long long)(T & 0xffffff);
+  const double r = fma((double)thi, 16777216.0, (double)tlo);
+  dst[idx] = r * scale_down((c < IM_NV) ? eamax[0] : eamax[1]);
+}
+
+// mT[f][w] bit j = observation 32 w + j misses feature f (transposed copy of mbits; constant over the EM iterations)
+__global__ void __launch_bounds__(256) masked_bits_transpose_kernel(const uint32_t* __restrict__ mbits, int wpr, int64_t n_obs,
+                                                                    uint32_t* __restrict__ mT, int64_t nwT) {
+  const int lane = threadIdx.x & 31;
+  const int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (blk * 32 >= n_obs) return;
+  const int64_t n = blk * 32 + lane;
+  for (int wd = 0; wd < wpr; ++wd) {
+    const uint32_t wv = (n < n_obs) ? mbits[n * wpr + wd] : 0u;
+    uint32_t keep = 0u;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t m = __ballot_sync(0xffffffffu, (wv >> b) & 1u);
+      if (lane == b) keep = m;
+    }
+    mT[(int64_t)(wd * 32 + lane) * nwT + blk] = keep;
+  }
+}
+
+ImmaPlan make_plan(const ShardState& sh) {
+  const int per8 = std::max(2, 2 * sm_count(sh.dev) / 8);
+  const int64_t nchunks = ceil_div(sh.n, (int64_t)IM_CHUNK);
+  ImmaPlan pl;
+  pl.s9 = std::max(1, per8 * 8 / 17);
+  pl.s10 = std::max(1, per8 - pl.s9);
+  pl.s9 = (int)std::min<int64_t>(pl.s9, nchunks);
+  pl.s10 = (int)std::min<int64_t>(pl.s10, nchunks);
+  return pl;
+}
+
+template <int DD>
+int launch_imma(ShardState& sh, double* dst) {
+  const ImmaPlan pl = make_plan(sh);
+  const int ncta = IM_G10 * pl.s10 + (16 - IM_G10) * pl.s9;
+  const int smem = 2 * IM_LDP * IM_PITCH;
+  int* ipart = reinterpret_cast<int*>(sh.partials);
+  unsigned long long* tpart = reinterpret_cast<unsigned long long*>(ipart + (int64_t)ncta * DD * IM_LDP);
+  GP_LAUNCH((masked_miss_imma_kernel<DD>), ncta, 256, smem, sh.st, sh.EA, sh.mbitsT, sh.nwT, sh.n, pl, sh.eamax, ipart, tpart,
+            sh.par.scal);
+  GP_LAUNCH(masked_miss_imma_finalize, (unsigned)ceil_div((int64_t)(DD + 1) * IM_EAS, 256), 256, 0, sh.st, ipart, tpart, DD, pl, sh.n,
+            sh.eamax, dst, sh.par.scal);
+  return GPLVM_OK;
+}
+
+}  // namespace
+
+// transposed mask bits for the INT8 complement sums (once per data set)
+int masked_imma_prepare(gplvm_ppca_session* s, ShardState& sh) {
+  CUDA_TRY(cudaMemsetAsync(sh.mbitsT, 0, sizeof(uint32_t) * (size_t)s->D * sh.nwT, sh.st));
+  CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 2 * sizeof(uint32_t), sh.st));
+  GP_LAUNCH(masked_bits_transpose_kernel, (unsigned)ceil_div(sh.n, (int64_t)256), 256, 0, sh.st, sh.mbits, s->WPR, sh.n, sh.mbitsT, sh.nwT);
+  return GPLVM_OK;
+}
+
+// complement sums [G^miss | S1^miss] (D x 152) + totals (152) into dst (length (D + 1) x 152)
+int masked_imma_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
+  switch (s->D) {
+    case 128: return launch_imma<128>(sh, dst);
+    case 256: return launch_imma<256>(sh, dst);
+    default: return fail(GPLVM_ERR_STATE, "INT8 masked statistics: unsupported D");
+  }
+}
+
+}  // namespace gplvm

@@ -63,6 +63,9 @@ struct ShardState {
   double* EA = nullptr;        // masked: n x EAS, row i = [vech(A_i) (NV) | ez_i (M)], A_i = ez ez^T + sigma2 Minv_i
   double* yy = nullptr;        // masked fused path: |(y_i - mu)_observed|^2 per observation
   uint32_t* mbits = nullptr;   // masked: n x WPR words, bit d set = feature d of the observation is missing
+  uint32_t* mbitsT = nullptr;  // masked fused path: D x nwT words, bit j of word w = observation 32 w + j misses the feature
+  int64_t nwT = 0;             //   4 x ceil(n / 128) words per feature
+  uint32_t* eamax = nullptr;   // masked fused path: high words of max |vech A| and max |ez| of the last solve
   double* parblock = nullptr;  // parameter block
   double* stats = nullptr;     // packed statistics (all-reduced), `S` doubles
   double* partials = nullptr;  // nparts x S
@@ -110,6 +113,8 @@ int dense_dmma_release(gplvm_ppca_session* s);
 int masked_dmma_b(gplvm_ppca_session* s, ShardState& sh, const double* W, const double* mu, double* bout, double* yyout);
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out);
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
+int masked_imma_prepare(gplvm_ppca_session* s, ShardState& sh);
+int masked_imma_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
 int masked_dmma_s2(gplvm_ppca_session* s, ShardState& sh, const double* ez, int64_t ldez, double* dst);
 int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
 // masked.cu

@@ -86,7 +86,7 @@ int64_t chunk_obs(int64_t D) {
 
 void free_shard(ShardState& sh) {
   cudaSetDevice(sh.dev);
-  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
+  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.mbitsT); cudaFree(sh.eamax); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
   cudaFree(sh.partials); cudaFree(sh.scratch);
   if (sh.tmap) free(sh.tmap);
   if (sh.ev0) cudaEventDestroy(sh.ev0);
@@ -286,6 +286,11 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
     if (e == cudaSuccess && s->missing && s->use_dmma) e = cudaMalloc(&sh.yy, sizeof(double) * (size_t)sh.n);
     if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.EA, sizeof(double) * ((size_t)sh.n * s->EAS + 8));
     if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.mbits, sizeof(uint32_t) * (size_t)(sh.n + 64) * s->WPR + 64);  // padded: whole-tile bulk copies
+    if (e == cudaSuccess && s->missing && s->use_dmma && (D == 128 || D == 256)) {
+      sh.nwT = 4 * ceil_div(sh.n, (int64_t)128);
+      e = cudaMalloc(&sh.mbitsT, sizeof(uint32_t) * (size_t)D * sh.nwT);
+      if (e == cudaSuccess) e = cudaMalloc(&sh.eamax, 256);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&sh.parblock, sizeof(double) * parlen);
     if (e == cudaSuccess) e = cudaMemset(sh.parblock, 0, sizeof(double) * parlen);
     if (e == cudaSuccess) e = cudaMalloc(&sh.stats, sizeof(double) * (size_t)std::max<int64_t>(s->S, 3 * D));
