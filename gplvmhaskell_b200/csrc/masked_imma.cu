@@ -34,6 +34,8 @@ constexpr int IM_PITCH = 160;       // bytes per tile row (128 + 32: rows 4 apar
 constexpr int IM_LDP = 72;          // int32 columns per feature row in the per-CTA partial block
 constexpr int IM_EAS = 152;
 constexpr int IM_NV = 136;
+constexpr int IM_PF = 3;            // cp.async stages of the entries (prefetch distance: 2 chunks)
+constexpr int IM_STAGE_BYTES = (256 + 64) * 32;
 constexpr int IM_G10 = 8;           // groups 0..7: 10 columns each (0..79); groups 8..15: 9 columns each (80..151)
 
 __device__ __forceinline__ void imma_s8u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -103,22 +105,48 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0;
 
-  // cutting assignment: lane = group of 4 observations of the chunk, warp = column (warps 0 .. NC - 9 take a second one)
-  const int ca = w, cb = w + 8;
-  const bool has_b = cb < NC;
+  // cutting assignment: thread = (column tid & 7, observation quad tid >> 3); threads 0..63 also take column 8 + (tid & 1)
+  // for quad tid >> 1.  Per load instruction a warp touches 4 rows x 64 contiguous bytes.  Every thread stages ITS OWN
+  // entries two chunks ahead with 8-byte cp.async into private shared-memory slots (no registers, no extra barrier).
+  const int ca = tid & 7, kqa = tid >> 3;
+  const int cb = 8 + (tid & 1), kqb = (tid >> 1) & 31;
+  const bool has_b = (tid < 64) && (cb < NC);
   const uint32_t hA = eamax[0], hE = eamax[1];
   const double sca = scale_up((col0 + ca < IM_NV) ? hA : hE);
   const double scb = scale_up((col0 + cb < IM_NV) ? hA : hE);
   unsigned long long tlo[2] = {0ull, 0ull}, thi[2] = {0ull, 0ull};
-  const int kq = lane;
   // k-word (kq & 7) = 4 h + t' of k32 step (kq >> 3) is stored at word 2 t' + h: (b0, b1) of a fragment are one 64-bit load
-  const uint32_t kpos = (uint32_t)(((kq >> 3) * 8 + 2 * (kq & 3) + ((kq >> 2) & 1)) * 4);
+  auto kpos = [](int kq) { return (uint32_t)(((kq >> 3) * 8 + 2 * (kq & 3) + ((kq >> 2) & 1)) * 4); };
   const uint32_t smem_u = smem_u32(smem);
+  const uint32_t stage_u = smem_u + 2 * IM_LDP * IM_PITCH;          // IM_PF stages of (256 + 64) x 32 B private slots
+  const uint32_t slot_a = (uint32_t)(tid * 32), slot_b = (uint32_t)((256 + (tid & 63)) * 32);
   const uint32_t* mrow[MT][2];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int r = 0; r < 2; ++r) mrow[mt][r] = mT + (int64_t)(w * 16 * MT + mt * 16 + g + 8 * r) * nwT;
+
+  auto prefetch = [&](int64_t chunk) {
+    if (chunk < chunk_end) {
+      const uint32_t st = stage_u + (uint32_t)((chunk - chunk_begin) % IM_PF) * IM_STAGE_BYTES;
+      const int64_t oa = chunk * IM_CHUNK + 4 * kqa, ob = chunk * IM_CHUNK + 4 * kqb;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double* src = EA + min(oa + r, n_obs - 1) * IM_EAS + col0 + ca;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + slot_a + 8 * r), "l"(src) : "memory");
+      }
+      if (has_b) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double* src = EA + min(ob + r, n_obs - 1) * IM_EAS + col0 + cb;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + slot_b + 8 * r), "l"(src) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per chunk, empty past the end
+  };
+  prefetch(chunk_begin);
+  prefetch(chunk_begin + 1);
 
   for (int64_t chunk = chunk_begin; chunk < chunk_end; ++chunk) {
     const uint32_t tile_u = smem_u + (uint32_t)(((chunk - chunk_begin) & 1) * NROW * IM_PITCH);
@@ -127,16 +155,21 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int r = 0; r < 2; ++r) mk[mt][r] = __ldg(reinterpret_cast<const uint4*>(mrow[mt][r] + chunk * 4));
-    const int64_t o0 = chunk * IM_CHUNK + 4 * kq;
-    double va[4], vb[4];
+    prefetch(chunk + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");     // this thread's entries of `chunk` have landed
+    {
+      const uint32_t st = stage_u + (uint32_t)((chunk - chunk_begin) % IM_PF) * IM_STAGE_BYTES;
+      double va[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t oi = min(o0 + r, n_obs - 1);
-      va[r] = EA[oi * IM_EAS + col0 + ca];
-      vb[r] = has_b ? EA[oi * IM_EAS + col0 + cb] : 0.0;
+      for (int r = 0; r < 4; ++r) va[r] = lds64(st + slot_a + 8 * r);
+      cut_store(va, sca, chunk * IM_CHUNK + 4 * kqa, n_obs, tile_u + (uint32_t)(ca * NSL * IM_PITCH) + kpos(kqa), tlo[0], thi[0]);
+      if (has_b) {
+        double vb[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) vb[r] = lds64(st + slot_b + 8 * r);
+        cut_store(vb, scb, chunk * IM_CHUNK + 4 * kqb, n_obs, tile_u + (uint32_t)(cb * NSL * IM_PITCH) + kpos(kqb), tlo[1], thi[1]);
+      }
     }
-    cut_store(va, sca, o0, n_obs, tile_u + (uint32_t)(ca * NSL * IM_PITCH) + kpos, tlo[0], thi[0]);
-    if (has_b) cut_store(vb, scb, o0, n_obs, tile_u + (uint32_t)(cb * NSL * IM_PITCH) + kpos, tlo[1], thi[1]);
     __syncthreads();   // tile complete; every warp finished the MMAs of the previous use of the other buffer
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -170,21 +203,34 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
       *reinterpret_cast<int2*>(&ipart[(int64_t)f * IM_LDP + nt * 8 + 2 * t]) = make_int2(acc[mt][nt][0], acc[mt][nt][1]);
       *reinterpret_cast<int2*>(&ipart[(int64_t)(f + 8) * IM_LDP + nt * 8 + 2 * t]) = make_int2(acc[mt][nt][2], acc[mt][nt][3]);
     }
+  // totals: column tid & 7 is shared by the lanes 8 apart (o = 8, 16) and by all 8 warps; column 8 + (tid & 1) by the
+  // lanes 2 apart of warps 0 and 1.  Integer sums: any order gives the same result.
+  __syncthreads();
+  unsigned long long* tred = reinterpret_cast<unsigned long long*>(smem);   // [8 warps][10 columns][2]
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      tlo[q] += __shfl_xor_sync(0xffffffffu, tlo[q], o);
-      thi[q] += __shfl_xor_sync(0xffffffffu, thi[q], o);
-    }
+  for (int o = 8; o <= 16; o <<= 1) {
+    tlo[0] += __shfl_xor_sync(0xffffffffu, tlo[0], o);
+    thi[0] += __shfl_xor_sync(0xffffffffu, thi[0], o);
   }
-  if (lane == 0) {
-    tpart[ca * 2] = tlo[0];
-    tpart[ca * 2 + 1] = thi[0];
-    if (has_b) {
-      tpart[cb * 2] = tlo[1];
-      tpart[cb * 2 + 1] = thi[1];
-    }
+#pragma unroll
+  for (int o = 2; o <= 16; o <<= 1) {
+    tlo[1] += __shfl_xor_sync(0xffffffffu, tlo[1], o);
+    thi[1] += __shfl_xor_sync(0xffffffffu, thi[1], o);
+  }
+  if (lane < 8) {
+    tred[(w * 10 + lane) * 2] = tlo[0];
+    tred[(w * 10 + lane) * 2 + 1] = thi[0];
+  }
+  if (lane < 2) {
+    tred[(w * 10 + 8 + lane) * 2] = (w < 2) ? tlo[1] : 0ull;
+    tred[(w * 10 + 8 + lane) * 2 + 1] = (w < 2) ? thi[1] : 0ull;
+  }
+  __syncthreads();
+  if (tid < 20) {
+    unsigned long long acc64 = 0ull;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc64 += tred[q * 20 + tid];
+    tpart[tid] = acc64;
   }
 }
 
@@ -300,9 +346,14 @@ template <int DD>
 int launch_imma(ShardState& sh, double* dst) {
   const ImmaPlan pl = make_plan(sh);
   const int ncta = IM_G10 * pl.s10 + (16 - IM_G10) * pl.s9;
-  const int smem = 2 * IM_LDP * IM_PITCH;
+  const int smem = 2 * IM_LDP * IM_PITCH + IM_PF * IM_STAGE_BYTES;   // 23 040 + 30 720 B
   int* ipart = reinterpret_cast<int*>(sh.partials);
   unsigned long long* tpart = reinterpret_cast<unsigned long long*>(ipart + (int64_t)ncta * DD * IM_LDP);
+  static bool attr_done[64] = {};
+  if (!attr_done[sh.dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute((masked_miss_imma_kernel<DD>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done[sh.dev & 63] = true;
+  }
   GP_LAUNCH((masked_miss_imma_kernel<DD>), ncta, 256, smem, sh.st, sh.EA, sh.mbitsT, sh.nwT, sh.n, pl, sh.eamax, ipart, tpart,
             sh.par.scal);
   GP_LAUNCH(masked_miss_imma_finalize, (unsigned)ceil_div((int64_t)(DD + 1) * IM_EAS, 256), 256, 0, sh.st, ipart, tpart, DD, pl, sh.n,
