@@ -36,6 +36,7 @@ constexpr int IM_EAS = 152;
 constexpr int IM_NV = 136;
 constexpr int IM_PF = 3;            // cp.async stages of the entries (prefetch distance: 2 chunks)
 constexpr int IM_STAGE_BYTES = (256 + 64) * 32;
+constexpr int IM_MS = 4;            // stages of the mask words (DD x 16 B each)
 constexpr int IM_G10 = 8;           // groups 0..7: 10 columns each (0..79); groups 8..15: 9 columns each (80..151)
 
 __device__ __forceinline__ void imma_s8u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -43,9 +44,6 @@ __device__ __forceinline__ void imma_s8u8(int (&c)[4], const uint32_t (&a)[4], u
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// 4 mask bits -> 4 bytes of 0 / 1 (bit i lands at position 8 i; the 16 partial products never collide)
-__device__ __forceinline__ uint32_t expand4(uint32_t x) { return ((x & 15u) * 0x00204081u) & 0x01010101u; }
-
 // biased exponent of the class maximum, clamped so that both 2^(51 - E) and 2^(E - 51) are normal numbers
 __device__ __forceinline__ int class_exponent(uint32_t hmax) {
   int ex = (int)((hmax >> 20) & 0x7ffu);
@@ -61,16 +59,24 @@ __device__ __forceinline__ double scale_down(uint32_t hmax) {    // 2^(E - FXP)
 // cuts 4 consecutive observations of one column into byte planes and stores plane s as one 32-bit word
 __device__ __forceinline__ void cut_store(const double (&v)[4], double sc, int64_t o0, int64_t n_obs, uint32_t dst,
                                           unsigned long long& tlo, unsigned long long& thi) {
+  const int nvalid = (int)min((int64_t)4, max((int64_t)0, n_obs - o0));   // observations past the end: masked out, not totalled
   uint32_t lo[4], hi[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const double y = fma(v[r], sc, 6755399441055744.0);   // 2^52 + 2^51: the mantissa of y is the integer x + 2^51
     lo[r] = (uint32_t)__double2loint(y);
     hi[r] = (uint32_t)__double2hiint(y) - 0x43300000u;
-    if (o0 + r < n_obs) {
-      tlo += lo[r];
-      thi += hi[r];
-    }
+  }
+  if (nvalid == 4) {   // hi <= 2^20: the four high words add in 32 bits
+    tlo += ((unsigned long long)lo[0] + lo[1]) + ((unsigned long long)lo[2] + lo[3]);
+    thi += (hi[0] + hi[1]) + (hi[2] + hi[3]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r < nvalid) {
+        tlo += lo[r];
+        thi += hi[r];
+      }
   }
 #pragma unroll
   for (int s = 0; s < NSL; ++s) {
@@ -87,7 +93,9 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
                                                int64_t n_obs, int col0, int64_t chunk_begin, int64_t chunk_end,
                                                const uint32_t* __restrict__ eamax, int* __restrict__ ipart,
                                                unsigned long long* __restrict__ tpart, uint8_t* smem) {
-  constexpr int MT = DD / 128;                     // m16 tiles per warp (8 warps cover DD features)
+  // warp tile: MT m16 tiles (DD / 8 features) x all NT n8 tiles.  (A 64-feature x NT / 2 warp tile halves the B-fragment
+  // loads but doubles the A-fragment work and measured slower: 8.1 ms vs 6.8 ms.)
+  constexpr int MT = DD / 128;
   constexpr int NT = (NC * NSL + 1 + 7) / 8;       // n8 tiles: NC x 7 byte planes + the count column
   constexpr int NROW = NT * 8;
   static_assert(NROW <= IM_LDP, "partial block pitch");
@@ -105,10 +113,12 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0;
 
-  // cutting assignment: thread = (column tid & 7, observation quad tid >> 3); threads 0..63 also take column 8 + (tid & 1)
-  // for quad tid >> 1.  Per load instruction a warp touches 4 rows x 64 contiguous bytes.  Every thread stages ITS OWN
-  // entries two chunks ahead with 8-byte cp.async into private shared-memory slots (no registers, no extra barrier).
-  const int ca = tid & 7, kqa = tid >> 3;
+  // cutting assignment: thread = (column (tid & 3) + 4 (tid >> 7), observation quad (tid >> 2) & 31): a warp covers 4
+  // columns x 8 consecutive quads, so its plane stores hit 32 different banks (column offsets {0, 24, 16, 8} words + the
+  // 8 words of one k32 step) and each load instruction touches 8 rows x 32 contiguous bytes.  Threads 0..63 also take
+  // column 8 + (tid & 1) for quad tid >> 1.  Every thread stages ITS OWN entries two chunks ahead with 8-byte cp.async
+  // into private shared-memory slots ([row][thread]: conflict-free; no registers, no extra barrier).
+  const int ca = (tid & 3) + 4 * (tid >> 7), kqa = (tid >> 2) & 31;
   const int cb = 8 + (tid & 1), kqb = (tid >> 1) & 31;
   const bool has_b = (tid < 64) && (cb < NC);
   const uint32_t hA = eamax[0], hE = eamax[1];
@@ -119,69 +129,83 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
   auto kpos = [](int kq) { return (uint32_t)(((kq >> 3) * 8 + 2 * (kq & 3) + ((kq >> 2) & 1)) * 4); };
   const uint32_t smem_u = smem_u32(smem);
   const uint32_t stage_u = smem_u + 2 * IM_LDP * IM_PITCH;          // IM_PF stages of (256 + 64) x 32 B private slots
-  const uint32_t slot_a = (uint32_t)(tid * 32), slot_b = (uint32_t)((256 + (tid & 63)) * 32);
-  const uint32_t* mrow[MT][2];
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) mrow[mt][r] = mT + (int64_t)(w * 16 * MT + mt * 16 + g + 8 * r) * nwT;
+  const uint32_t slot_a = (uint32_t)(tid * 8), slot_b = (uint32_t)(4 * 2048 + (tid & 63) * 8);   // + 2048 r / + 512 r
+  // mask words of a chunk: one contiguous DD x 16 B block, copied 2 chunks ahead (16 B per thread) into one of IM_MS
+  // stages; stage (i + 2) % 4 was last read in the MMA phase of chunk i - 2, which every warp left before barrier i - 1
+  const uint32_t mask_u = stage_u + IM_PF * IM_STAGE_BYTES;
+  (void)nwT;
 
+  // EA is allocated in whole chunks (session.cu), so the last chunk may be read past n_obs: those entries meet zero mask
+  // bits and are left out of the totals (nvalid in cut_store)
+  const double* pa = EA + (chunk_begin * IM_CHUNK + 4 * kqa) * IM_EAS + col0 + ca;
+  const double* pb = EA + (chunk_begin * IM_CHUNK + 4 * kqb) * IM_EAS + col0 + cb;
+  const uint32_t* pm = mT + (chunk_begin * DD + (tid % DD)) * 4;
+  int pf_stage = 0, pf_mstage = 0;
   auto prefetch = [&](int64_t chunk) {
     if (chunk < chunk_end) {
-      const uint32_t st = stage_u + (uint32_t)((chunk - chunk_begin) % IM_PF) * IM_STAGE_BYTES;
-      const int64_t oa = chunk * IM_CHUNK + 4 * kqa, ob = chunk * IM_CHUNK + 4 * kqb;
+      const uint32_t st = stage_u + (uint32_t)pf_stage * IM_STAGE_BYTES;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const double* src = EA + min(oa + r, n_obs - 1) * IM_EAS + col0 + ca;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + slot_a + 8 * r), "l"(src) : "memory");
-      }
+      for (int r = 0; r < 4; ++r)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + slot_a + 2048 * r), "l"(pa + r * IM_EAS) : "memory");
       if (has_b) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const double* src = EA + min(ob + r, n_obs - 1) * IM_EAS + col0 + cb;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + slot_b + 8 * r), "l"(src) : "memory");
-        }
+        for (int r = 0; r < 4; ++r)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + slot_b + 512 * r), "l"(pb + r * IM_EAS) : "memory");
       }
+      if (tid < DD)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mask_u + (uint32_t)(pf_mstage * DD * 16 + tid * 16)), "l"(pm)
+                     : "memory");
+      pa += IM_CHUNK * IM_EAS;
+      pb += IM_CHUNK * IM_EAS;
+      pm += DD * 4;
+      pf_stage = (pf_stage + 1 == IM_PF) ? 0 : pf_stage + 1;
+      pf_mstage = (pf_mstage + 1) & (IM_MS - 1);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // one group per chunk, empty past the end
   };
   prefetch(chunk_begin);
   prefetch(chunk_begin + 1);
 
+  int cs = 0, cms = 0, cbuf = 0;
   for (int64_t chunk = chunk_begin; chunk < chunk_end; ++chunk) {
-    const uint32_t tile_u = smem_u + (uint32_t)(((chunk - chunk_begin) & 1) * NROW * IM_PITCH);
-    uint4 mk[MT][2];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int r = 0; r < 2; ++r) mk[mt][r] = __ldg(reinterpret_cast<const uint4*>(mrow[mt][r] + chunk * 4));
+    const uint32_t tile_u = smem_u + (uint32_t)(cbuf * NROW * IM_PITCH);
     prefetch(chunk + 2);
     asm volatile("cp.async.wait_group 2;" ::: "memory");     // this thread's entries of `chunk` have landed
     {
-      const uint32_t st = stage_u + (uint32_t)((chunk - chunk_begin) % IM_PF) * IM_STAGE_BYTES;
+      const uint32_t st = stage_u + (uint32_t)cs * IM_STAGE_BYTES;
       double va[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) va[r] = lds64(st + slot_a + 8 * r);
+      for (int r = 0; r < 4; ++r) va[r] = lds64(st + slot_a + 2048 * r);
       cut_store(va, sca, chunk * IM_CHUNK + 4 * kqa, n_obs, tile_u + (uint32_t)(ca * NSL * IM_PITCH) + kpos(kqa), tlo[0], thi[0]);
       if (has_b) {
         double vb[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) vb[r] = lds64(st + slot_b + 8 * r);
+        for (int r = 0; r < 4; ++r) vb[r] = lds64(st + slot_b + 512 * r);
         cut_store(vb, scb, chunk * IM_CHUNK + 4 * kqb, n_obs, tile_u + (uint32_t)(cb * NSL * IM_PITCH) + kpos(kqb), tlo[1], thi[1]);
       }
     }
-    __syncthreads();   // tile complete; every warp finished the MMAs of the previous use of the other buffer
+    __syncthreads();   // tile + mask words complete; every warp finished the MMAs of the previous use of the other buffer
+    uint32_t mk[MT][2];   // this lane's 32 mask bits of rows g and g + 8 (fragment order, see the transpose kernel)
+    {
+      const uint32_t mst = mask_u + (uint32_t)(cms * DD * 16);
+      cs = (cs + 1 == IM_PF) ? 0 : cs + 1;
+      cms = (cms + 1) & (IM_MS - 1);
+      cbuf ^= 1;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mk[mt][r]) : "r"(mst + (uint32_t)((w * 16 * MT + mt * 16 + g + 8 * r) * 16 + 4 * t)));
+    }
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t a[MT][4];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const uint32_t w0 = (ks == 0) ? mk[mt][0].x : (ks == 1) ? mk[mt][0].y : (ks == 2) ? mk[mt][0].z : mk[mt][0].w;
-        const uint32_t w1 = (ks == 0) ? mk[mt][1].x : (ks == 1) ? mk[mt][1].y : (ks == 2) ? mk[mt][1].z : mk[mt][1].w;
-        a[mt][0] = expand4(w0 >> (4 * t));
-        a[mt][1] = expand4(w1 >> (4 * t));
-        a[mt][2] = expand4(w0 >> (16 + 4 * t));
-        a[mt][3] = expand4(w1 >> (16 + 4 * t));
+        a[mt][0] = (mk[mt][0] >> (2 * ks)) & 0x01010101u;
+        a[mt][1] = (mk[mt][1] >> (2 * ks)) & 0x01010101u;
+        a[mt][2] = (mk[mt][0] >> (2 * ks + 1)) & 0x01010101u;
+        a[mt][3] = (mk[mt][1] >> (2 * ks + 1)) & 0x01010101u;
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
@@ -203,12 +227,12 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
       *reinterpret_cast<int2*>(&ipart[(int64_t)f * IM_LDP + nt * 8 + 2 * t]) = make_int2(acc[mt][nt][0], acc[mt][nt][1]);
       *reinterpret_cast<int2*>(&ipart[(int64_t)(f + 8) * IM_LDP + nt * 8 + 2 * t]) = make_int2(acc[mt][nt][2], acc[mt][nt][3]);
     }
-  // totals: column tid & 7 is shared by the lanes 8 apart (o = 8, 16) and by all 8 warps; column 8 + (tid & 1) by the
-  // lanes 2 apart of warps 0 and 1.  Integer sums: any order gives the same result.
+  // totals: within a warp the lanes with equal (lane & 3) share a column, warps 0..3 hold columns 0..3 and warps 4..7
+  // columns 4..7; column 8 + (lane & 1) lives in warps 0 and 1.  Integer sums: any order gives the same result.
   __syncthreads();
-  unsigned long long* tred = reinterpret_cast<unsigned long long*>(smem);   // [8 warps][10 columns][2]
+  unsigned long long* tred = reinterpret_cast<unsigned long long*>(smem);   // [8 warps][6 columns][2]
 #pragma unroll
-  for (int o = 8; o <= 16; o <<= 1) {
+  for (int o = 4; o <= 16; o <<= 1) {
     tlo[0] += __shfl_xor_sync(0xffffffffu, tlo[0], o);
     thi[0] += __shfl_xor_sync(0xffffffffu, thi[0], o);
   }
@@ -217,19 +241,25 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
     tlo[1] += __shfl_xor_sync(0xffffffffu, tlo[1], o);
     thi[1] += __shfl_xor_sync(0xffffffffu, thi[1], o);
   }
-  if (lane < 8) {
-    tred[(w * 10 + lane) * 2] = tlo[0];
-    tred[(w * 10 + lane) * 2 + 1] = thi[0];
+  if (lane < 4) {
+    tred[(w * 6 + lane) * 2] = tlo[0];
+    tred[(w * 6 + lane) * 2 + 1] = thi[0];
   }
   if (lane < 2) {
-    tred[(w * 10 + 8 + lane) * 2] = (w < 2) ? tlo[1] : 0ull;
-    tred[(w * 10 + 8 + lane) * 2 + 1] = (w < 2) ? thi[1] : 0ull;
+    tred[(w * 6 + 4 + lane) * 2] = tlo[1];     // zero outside warps 0 and 1
+    tred[(w * 6 + 4 + lane) * 2 + 1] = thi[1];
   }
   __syncthreads();
   if (tid < 20) {
+    const int c = tid >> 1, h = tid & 1;
     unsigned long long acc64 = 0ull;
+    if (c < 8) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc64 += tred[q * 20 + tid];
+      for (int q = 0; q < 4; ++q) acc64 += tred[(((c >> 2) * 4 + q) * 6 + (c & 3)) * 2 + h];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc64 += tred[((q * 6) + 4 + (c - 8)) * 2 + h];
+    }
     tpart[tid] = acc64;
   }
 }
@@ -312,14 +342,21 @@ __global__ void __launch_bounds__(256) masked_miss_imma_finalize(const int* __re
   dst[idx] = r * scale_down((c < IM_NV) ? eamax[0] : eamax[1]);
 }
 
-// mT[f][w] bit j = observation 32 w + j misses feature f (transposed copy of mbits; constant over the EM iterations)
+// Transposed copy of the mask bits in MMA-fragment order (constant over the EM iterations): one contiguous D x 16 B
+// block per 128-observation chunk; word t (0..3) of feature f holds the 32 observations that the lanes with
+// threadID_in_group = t need for their A fragments: bit 8 b + 2 ks + h  <=>  observation 32 ks + 16 h + 4 t + b of the
+// chunk.  (W >> (2 ks + h)) & 0x01010101 is then the s8 fragment register of k32 step ks, k half h.
 __global__ void __launch_bounds__(256) masked_bits_transpose_kernel(const uint32_t* __restrict__ mbits, int wpr, int64_t n_obs,
-                                                                    uint32_t* __restrict__ mT, int64_t nwT) {
+                                                                    uint32_t* __restrict__ mT, int64_t nchunks) {
   const int lane = threadIdx.x & 31;
-  const int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (blk * 32 >= n_obs) return;
-  const int64_t n = blk * 32 + lane;
-  for (int wd = 0; wd < wpr; ++wd) {
+  const int64_t wi = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);   // warp = (chunk, word of 32 features)
+  if (wi >= nchunks * wpr) return;
+  const int64_t chunk = wi / wpr;
+  const int wd = (int)(wi % wpr);
+  uint32_t S[4];   // lane b: bit i of S[ks] = observation 32 ks + i of the chunk misses feature 32 wd + b
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int64_t n = chunk * IM_CHUNK + ks * 32 + lane;
     const uint32_t wv = (n < n_obs) ? mbits[n * wpr + wd] : 0u;
     uint32_t keep = 0u;
 #pragma unroll
@@ -327,8 +364,21 @@ __global__ void __launch_bounds__(256) masked_bits_transpose_kernel(const uint32
       const uint32_t m = __ballot_sync(0xffffffffu, (wv >> b) & 1u);
       if (lane == b) keep = m;
     }
-    mT[(int64_t)(wd * 32 + lane) * nwT + blk] = keep;
+    S[ks] = keep;
   }
+  uint32_t out[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    uint32_t o = 0u;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) o |= ((S[ks] >> (16 * h + 4 * t + b)) & 1u) << (8 * b + 2 * ks + h);
+    out[t] = o;
+  }
+  *reinterpret_cast<uint4*>(&mT[((chunk * wpr + wd) * 32 + lane) * 4]) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 ImmaPlan make_plan(const ShardState& sh) {
@@ -346,7 +396,7 @@ template <int DD>
 int launch_imma(ShardState& sh, double* dst) {
   const ImmaPlan pl = make_plan(sh);
   const int ncta = IM_G10 * pl.s10 + (16 - IM_G10) * pl.s9;
-  const int smem = 2 * IM_LDP * IM_PITCH + IM_PF * IM_STAGE_BYTES;   // 23 040 + 30 720 B
+  const int smem = 2 * IM_LDP * IM_PITCH + IM_PF * IM_STAGE_BYTES + IM_MS * DD * 16;   // 23 040 + 30 720 + 16 384 B
   int* ipart = reinterpret_cast<int*>(sh.partials);
   unsigned long long* tpart = reinterpret_cast<unsigned long long*>(ipart + (int64_t)ncta * DD * IM_LDP);
   static bool attr_done[64] = {};
@@ -365,9 +415,10 @@ int launch_imma(ShardState& sh, double* dst) {
 
 // transposed mask bits for the INT8 complement sums (once per data set)
 int masked_imma_prepare(gplvm_ppca_session* s, ShardState& sh) {
-  CUDA_TRY(cudaMemsetAsync(sh.mbitsT, 0, sizeof(uint32_t) * (size_t)s->D * sh.nwT, sh.st));
   CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 2 * sizeof(uint32_t), sh.st));
-  GP_LAUNCH(masked_bits_transpose_kernel, (unsigned)ceil_div(sh.n, (int64_t)256), 256, 0, sh.st, sh.mbits, s->WPR, sh.n, sh.mbitsT, sh.nwT);
+  const int64_t nchunks = sh.nwT / 4;
+  GP_LAUNCH(masked_bits_transpose_kernel, (unsigned)ceil_div(nchunks * s->WPR, (int64_t)8), 256, 0, sh.st, sh.mbits, s->WPR, sh.n,
+            sh.mbitsT, nchunks);
   return GPLVM_OK;
 }
 

@@ -284,7 +284,7 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
     if (e == cudaSuccess) e = cudaMalloc(&sh.X, sizeof(double) * (size_t)sh.n * sh.ldx);
     if (e == cudaSuccess && (s->missing == s->use_dmma)) e = cudaMalloc(&sh.Ez, sizeof(double) * (size_t)sh.n * MP);  // generic dense Ez / fused masked b
     if (e == cudaSuccess && s->missing && s->use_dmma) e = cudaMalloc(&sh.yy, sizeof(double) * (size_t)sh.n);
-    if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.EA, sizeof(double) * ((size_t)sh.n * s->EAS + 8));
+    if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.EA, sizeof(double) * ((size_t)round_up(sh.n, 128) * s->EAS + 8));  // whole 128-observation chunks (masked_imma.cu)
     if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.mbits, sizeof(uint32_t) * (size_t)(sh.n + 64) * s->WPR + 64);  // padded: whole-tile bulk copies
     if (e == cudaSuccess && s->missing && s->use_dmma && (D == 128 || D == 256)) {
       sh.nwT = 4 * ceil_div(sh.n, (int64_t)128);

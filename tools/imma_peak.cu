@@ -28,6 +28,62 @@ __global__ void __launch_bounds__(256) probe(int iters, int* out, uint32_t seed)
   if (s == 0x7fffffff) out[0] = s;
 }
 
+// the register pattern of masked_imma.cu's inner loop: 2 A fragments x 9 B fragments, 18 accumulators, no memory traffic
+template <bool MT_OUTER>
+__global__ void __launch_bounds__(256, 2) probe_tile(int iters, int* out, const uint32_t* __restrict__ src) {
+  int c[2][9][4];
+  uint32_t a[2][4], b[9][2];
+  for (int m = 0; m < 2; ++m)
+    for (int i = 0; i < 4; ++i) a[m][i] = src[threadIdx.x + 256 * (m * 4 + i)];
+  for (int n = 0; n < 9; ++n)
+    for (int i = 0; i < 2; ++i) b[n][i] = src[threadIdx.x + 256 * (8 + n * 2 + i)];
+  for (int m = 0; m < 2; ++m)
+    for (int n = 0; n < 9; ++n)
+      for (int i = 0; i < 4; ++i) c[m][n][i] = 0;
+  for (int it = 0; it < iters; ++it) {
+    if (MT_OUTER) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 9; ++n) imma(c[m][n], a[m], b[n]);
+    } else {
+#pragma unroll
+      for (int n = 0; n < 9; ++n)
+#pragma unroll
+        for (int m = 0; m < 2; ++m) imma(c[m][n], a[m], b[n]);
+    }
+  }
+  int s = 0;
+  for (int m = 0; m < 2; ++m)
+    for (int n = 0; n < 9; ++n)
+      for (int i = 0; i < 4; ++i) s += c[m][n][i];
+  if (s == 0x7fffffff) out[0] = s;
+}
+
+template <bool MT_OUTER>
+void run_tile(int sms) {
+  int* out;
+  uint32_t* src;
+  cudaMalloc(&out, 4);
+  cudaMalloc(&src, 256 * 32 * 4);
+  cudaMemset(src, 1, 256 * 32 * 4);
+  const int iters = 20000;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  probe_tile<MT_OUTER><<<sms * 2, 256>>>(100, out, src);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  probe_tile<MT_OUTER><<<sms * 2, 256>>>(iters, out, src);
+  cudaEventRecord(e1);
+  cudaDeviceSynchronize();
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double ops = (double)sms * 2 * 8 * iters * 18 * 16.0 * 8 * 32 * 2;
+  printf("IMMA tile 2x9 (%s outer), 2 CTAs/SM: %.3f ms  %.1f TOPS  (%s)\n", MT_OUTER ? "m" : "n", ms, ops / ms * 1e-9,
+         cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int CHAINS>
 void run(int ctas_per_sm, int sms) {
   int* out;
@@ -58,5 +114,7 @@ int main() {
   run<8>(1, p.multiProcessorCount);
   run<16>(1, p.multiProcessorCount);
   run<16>(2, p.multiProcessorCount);
+  run_tile<false>(p.multiProcessorCount);
+  run_tile<true>(p.multiProcessorCount);
   return 0;
 }
