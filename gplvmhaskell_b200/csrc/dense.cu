@@ -513,11 +513,11 @@ int splits_for(int64_t n_obs, int64_t unit, int tiles_xy) {
 
 }  // namespace
 
-int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst) {
+int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst, double* scal) {
   PeerArgs pa{nullptr, 1, 0, 0, 0ull, (long long)S};
   if (!dst && sh.peer_args.peers) pa = sh.peer_args;   // set by the dense step when the peer exchange is active
   GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(S, 32), 256, 0, sh.st, sh.partials, dst ? dst : sh.stats, S, nparts,
-            sh.par.scal, pa);
+            scal ? scal : sh.par.scal, pa);
   return GPLVM_OK;
 }
 

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256, 1) masked_miss_dmma_kernel(const double* 
 }
 
 template <int DD>
-int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart) {
+int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart, const double* scal) {
   const int smem = KB_STAGES * (KB_TR * EASF * 8 + KB_TR * (DD / 32) * 4) + 64;
   static bool attr_done[64] = {};
   if (!attr_done[sh.dev & 63]) {
@@ -396,8 +396,7 @@ int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart
     attr_done[sh.dev & 63] = true;
   }
   dim3 grid(rb, DD / 128 > 0 ? DD / 128 : 1);
-  GP_LAUNCH((masked_miss_dmma_kernel<DD>), grid, 256, smem, sh.st, sh.EA, sh.mbits, sh.n, rows_per_cta, sh.partials, Spart,
-            sh.par.scal);
+  GP_LAUNCH((masked_miss_dmma_kernel<DD>), grid, 256, smem, sh.st, sh.EA, sh.mbits, sh.n, rows_per_cta, sh.partials, Spart, scal);
   return GPLVM_OK;
 }
 
@@ -409,7 +408,7 @@ int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid)
     CUDA_TRY(cudaFuncSetAttribute((masked_solve_kernel<DD, LL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done[sh.dev & 63] = true;
   }
-  if (!LL && sh.eamax) CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 2 * sizeof(uint32_t), sh.st));
+  if (!LL && sh.eamax) CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 24, sh.st));   // class maxima + precision-guard counters
   GP_LAUNCH((masked_solve_kernel<DD, LL>), grid, SOLVE_WARPS * 32, smem, sh.st, bsrc, yy, sh.mbits, sh.n, sh.par, sh.EA, sh.partials,
             LL ? nullptr : sh.eamax);
   return GPLVM_OK;
@@ -433,12 +432,16 @@ int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc
 
 // complement sums [G^miss | S1^miss] (D x 152) + totals (152) into dst (length (D + 1) x 152)
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
-  // default: exact fixed-point sums on the INT8 tensor cores (masked_imma.cu); GPLVM_MISS_DMMA=1 keeps the FP64 DMMA product
-  static const bool use_dmma = []() {
+  // default: exact fixed-point sums on the INT8 tensor cores (masked_imma.cu), followed by the FP64 DMMA product as a
+  // device-side fallback that runs only when the precision guard of the INT8 path fired (its `scal` block is the guard's:
+  // S_DONE = 1.0 makes both kernels return at once).  GPLVM_MISS_DMMA=1 selects the FP64 product unconditionally.
+  static const bool force_dmma = []() {
     const char* e = getenv("GPLVM_MISS_DMMA");
     return e ? (atoi(e) != 0) : false;
   }();
-  if (!use_dmma && sh.mbitsT) return masked_imma_miss_sums(s, sh, dst);
+  const bool imma = !force_dmma && sh.mbitsT;
+  if (imma) GP_TRY(masked_imma_miss_sums(s, sh, dst));
+  double* scal = imma ? masked_imma_guard_scal(sh) : sh.par.scal;
   const int64_t Spart = (int64_t)(s->D + 1) * EASF;
   const int fgroups = (int)std::max<int64_t>(1, s->D / 128);
   int rb = (int)std::min<int64_t>(std::max<int64_t>(1, sm_count(sh.dev) / fgroups), sh.nparts);
@@ -446,12 +449,12 @@ int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
   rb = (int)ceil_div(sh.n, rows_per_cta);
   int rc;
   switch (s->D) {
-    case 128: rc = launch_miss_dmma<128>(sh, rb, rows_per_cta, Spart); break;
-    case 256: rc = launch_miss_dmma<256>(sh, rb, rows_per_cta, Spart); break;
+    case 128: rc = launch_miss_dmma<128>(sh, rb, rows_per_cta, Spart, scal); break;
+    case 256: rc = launch_miss_dmma<256>(sh, rb, rows_per_cta, Spart, scal); break;
     default: return fail(GPLVM_ERR_STATE, "fused masked statistics: unsupported D");
   }
   GP_TRY(rc);
-  return launch_reduce_partials(sh, Spart, rb, dst);
+  return launch_reduce_partials(sh, Spart, rb, dst, scal);
 }
 
 }  // namespace gplvm

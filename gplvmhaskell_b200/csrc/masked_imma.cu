@@ -56,9 +56,23 @@ __device__ __forceinline__ double scale_down(uint32_t hmax) {    // 2^(E - FXP)
   return __hiloint2double((1023 - FXP - 1022 + class_exponent(hmax)) << 20, 0);
 }
 
+// eamax block (256 B, device): [0] / [1] high words of max |vech A| / max |ez| (solver), then two 64-bit counters of
+// entries that the fixed-point grid resolves poorly, then S_COUNT doubles used as the `scal` block of the FP64 fallback
+// kernels (slot S_DONE = 1.0: skip, the INT8 result stands).
+constexpr int IM_GUARD_BITS = 20;
+__host__ __device__ inline unsigned long long* guard_counts(uint32_t* eamax) { return reinterpret_cast<unsigned long long*>(eamax + 2); }
+__host__ __device__ inline double* guard_scal(uint32_t* eamax) { return reinterpret_cast<double*>(eamax + 16); }
+// more than 1 % of the entries of a class more than 2^20 below its maximum (an outlier sets the scale): the grid would
+// leave typical entries fewer than 32 bits, so this step's sums are redone in FP64 (masked_miss_dmma_kernel)
+__device__ __forceinline__ bool guard_fallback(const uint32_t* eamax, int64_t n_obs) {
+  const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(eamax + 2);
+  // the counters sample one observation in four
+  return cnt[0] * 400ull > (unsigned long long)n_obs * IM_NV || cnt[1] * 400ull > (unsigned long long)n_obs * (IM_EAS - IM_NV);
+}
+
 // cuts 4 consecutive observations of one column into byte planes and stores plane s as one 32-bit word
-__device__ __forceinline__ void cut_store(const double (&v)[4], double sc, int64_t o0, int64_t n_obs, uint32_t dst,
-                                          unsigned long long& tlo, unsigned long long& thi) {
+__device__ __forceinline__ void cut_store(const double (&v)[4], double sc, uint32_t thr, int64_t o0, int64_t n_obs, uint32_t dst,
+                                          unsigned long long& tlo, unsigned long long& thi, uint32_t& small) {
   const int nvalid = (int)min((int64_t)4, max((int64_t)0, n_obs - o0));   // observations past the end: masked out, not totalled
   uint32_t lo[4], hi[4];
 #pragma unroll
@@ -67,6 +81,9 @@ __device__ __forceinline__ void cut_store(const double (&v)[4], double sc, int64
     lo[r] = (uint32_t)__double2loint(y);
     hi[r] = (uint32_t)__double2hiint(y) - 0x43300000u;
   }
+  // precision guard, sampled on the first observation of every quad: entries more than 2^IM_GUARD_BITS below the class
+  // maximum keep fewer than 52 - IM_GUARD_BITS bits on the fixed-point grid
+  small += (((uint32_t)__double2hiint(v[0]) & 0x7fffffffu) < thr) ? 1u : 0u;
   if (nvalid == 4) {   // hi <= 2^20: the four high words add in 32 bits
     tlo += ((unsigned long long)lo[0] + lo[1]) + ((unsigned long long)lo[2] + lo[3]);
     thi += (hi[0] + hi[1]) + (hi[2] + hi[3]);
@@ -91,7 +108,7 @@ __device__ __forceinline__ void cut_store(const double (&v)[4], double sc, int64
 template <int DD, int NC>
 __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, const uint32_t* __restrict__ mT, int64_t nwT,
                                                int64_t n_obs, int col0, int64_t chunk_begin, int64_t chunk_end,
-                                               const uint32_t* __restrict__ eamax, int* __restrict__ ipart,
+                                               uint32_t* __restrict__ eamax, int* __restrict__ ipart,
                                                unsigned long long* __restrict__ tpart, uint8_t* smem) {
   // warp tile: MT m16 tiles (DD / 8 features) x all NT n8 tiles.  (A 64-feature x NT / 2 warp tile halves the B-fragment
   // loads but doubles the A-fragment work and measured slower: 8.1 ms vs 6.8 ms.)
@@ -125,6 +142,10 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
   const double sca = scale_up((col0 + ca < IM_NV) ? hA : hE);
   const double scb = scale_up((col0 + cb < IM_NV) ? hA : hE);
   unsigned long long tlo[2] = {0ull, 0ull}, thi[2] = {0ull, 0ull};
+  const bool a_is_A = col0 + ca < IM_NV, b_is_A = col0 + cb < IM_NV;
+  const uint32_t thra = (uint32_t)(class_exponent(a_is_A ? hA : hE) - IM_GUARD_BITS) << 20;
+  const uint32_t thrb = (uint32_t)(class_exponent(b_is_A ? hA : hE) - IM_GUARD_BITS) << 20;
+  uint32_t small[2] = {0u, 0u};
   // k-word (kq & 7) = 4 h + t' of k32 step (kq >> 3) is stored at word 2 t' + h: (b0, b1) of a fragment are one 64-bit load
   auto kpos = [](int kq) { return (uint32_t)(((kq >> 3) * 8 + 2 * (kq & 3) + ((kq >> 2) & 1)) * 4); };
   const uint32_t smem_u = smem_u32(smem);
@@ -176,12 +197,12 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
       double va[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) va[r] = lds64(st + slot_a + 2048 * r);
-      cut_store(va, sca, chunk * IM_CHUNK + 4 * kqa, n_obs, tile_u + (uint32_t)(ca * NSL * IM_PITCH) + kpos(kqa), tlo[0], thi[0]);
+      cut_store(va, sca, thra, chunk * IM_CHUNK + 4 * kqa, n_obs, tile_u + (uint32_t)(ca * NSL * IM_PITCH) + kpos(kqa), tlo[0], thi[0], small[0]);
       if (has_b) {
         double vb[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) vb[r] = lds64(st + slot_b + 512 * r);
-        cut_store(vb, scb, chunk * IM_CHUNK + 4 * kqb, n_obs, tile_u + (uint32_t)(cb * NSL * IM_PITCH) + kpos(kqb), tlo[1], thi[1]);
+        cut_store(vb, scb, thrb, chunk * IM_CHUNK + 4 * kqb, n_obs, tile_u + (uint32_t)(cb * NSL * IM_PITCH) + kpos(kqb), tlo[1], thi[1], small[1]);
       }
     }
     __syncthreads();   // tile + mask words complete; every warp finished the MMAs of the previous use of the other buffer
@@ -227,6 +248,14 @@ __device__ __forceinline__ void miss_imma_body(const double* __restrict__ EA, co
       *reinterpret_cast<int2*>(&ipart[(int64_t)f * IM_LDP + nt * 8 + 2 * t]) = make_int2(acc[mt][nt][0], acc[mt][nt][1]);
       *reinterpret_cast<int2*>(&ipart[(int64_t)(f + 8) * IM_LDP + nt * 8 + 2 * t]) = make_int2(acc[mt][nt][2], acc[mt][nt][3]);
     }
+  {  // precision-guard counters (integer atomics: order-independent)
+    const uint32_t sA = __reduce_add_sync(0xffffffffu, (a_is_A ? small[0] : 0u) + (b_is_A ? small[1] : 0u));
+    const uint32_t sE = __reduce_add_sync(0xffffffffu, (a_is_A ? 0u : small[0]) + (b_is_A ? 0u : small[1]));
+    if (lane == 0) {
+      if (sA) atomicAdd(guard_counts(eamax), (unsigned long long)sA);
+      if (sE) atomicAdd(guard_counts(eamax) + 1, (unsigned long long)sE);
+    }
+  }
   // totals: within a warp the lanes with equal (lane & 3) share a column, warps 0..3 hold columns 0..3 and warps 4..7
   // columns 4..7; column 8 + (lane & 1) lives in warps 0 and 1.  Integer sums: any order gives the same result.
   __syncthreads();
@@ -284,7 +313,7 @@ __host__ __device__ inline void imma_locate(const ImmaPlan& pl, int cta, int& gr
 template <int DD>
 __global__ void __launch_bounds__(256, 2) masked_miss_imma_kernel(const double* __restrict__ EA, const uint32_t* __restrict__ mT,
                                                                  int64_t nwT, int64_t n_obs, ImmaPlan pl,
-                                                                 const uint32_t* __restrict__ eamax, int* __restrict__ ipart,
+                                                                 uint32_t* __restrict__ eamax, int* __restrict__ ipart,
                                                                  unsigned long long* __restrict__ tpart,
                                                                  const double* __restrict__ scal) {
   if (scal[S_DONE] != 0.0) return;
@@ -303,11 +332,13 @@ __global__ void __launch_bounds__(256, 2) masked_miss_imma_kernel(const double* 
 
 // dst[f][c] (f < D: complement sums of feature f; f = D: totals over all observations), each rounded to FP64 once
 __global__ void __launch_bounds__(256) masked_miss_imma_finalize(const int* __restrict__ ipart, const unsigned long long* __restrict__ tpart,
-                                                                 int D, ImmaPlan pl, int64_t n_obs, const uint32_t* __restrict__ eamax,
+                                                                 int D, ImmaPlan pl, int64_t n_obs, uint32_t* __restrict__ eamax,
                                                                  double* __restrict__ dst, const double* __restrict__ scal) {
-  if (scal[S_DONE] != 0.0) return;
   const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= (D + 1) * IM_EAS) return;
+  const bool done = scal[S_DONE] != 0.0;
+  const bool fallback = !done && guard_fallback(eamax, n_obs);
+  if (idx == 0) guard_scal(eamax)[S_DONE] = fallback ? 0.0 : 1.0;   // 0.0: the FP64 kernels that follow redo the sums
+  if (done || fallback || idx >= (D + 1) * IM_EAS) return;
   const int f = idx / IM_EAS, c = idx % IM_EAS;
   const int group = (c < 80) ? c / 10 : IM_G10 + (c - 80) / 9;
   const int lc = (c < 80) ? c % 10 : (c - 80) % 9;
@@ -413,9 +444,11 @@ int launch_imma(ShardState& sh, double* dst) {
 
 }  // namespace
 
+double* masked_imma_guard_scal(ShardState& sh) { return guard_scal(sh.eamax); }
+
 // transposed mask bits for the INT8 complement sums (once per data set)
 int masked_imma_prepare(gplvm_ppca_session* s, ShardState& sh) {
-  CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 2 * sizeof(uint32_t), sh.st));
+  CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 256, sh.st));
   const int64_t nchunks = sh.nwT / 4;
   GP_LAUNCH(masked_bits_transpose_kernel, (unsigned)ceil_div(nchunks * s->WPR, (int64_t)8), 256, 0, sh.st, sh.mbits, s->WPR, sh.n,
             sh.mbitsT, nchunks);

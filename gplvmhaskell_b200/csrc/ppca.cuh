@@ -65,7 +65,7 @@ struct ShardState {
   uint32_t* mbits = nullptr;   // masked: n x WPR words, bit d set = feature d of the observation is missing
   uint32_t* mbitsT = nullptr;  // masked fused path: D x nwT words, bit j of word w = observation 32 w + j misses the feature
   int64_t nwT = 0;             //   4 x ceil(n / 128) words per feature
-  uint32_t* eamax = nullptr;   // masked fused path: high words of max |vech A| and max |ez| of the last solve
+  uint32_t* eamax = nullptr;   // masked fused path: 256 B block: class maxima of the last solve, precision-guard counters, guard flags (masked_imma.cu)
   double* parblock = nullptr;  // parameter block
   double* stats = nullptr;     // packed statistics (all-reduced), `S` doubles
   double* partials = nullptr;  // nparts x S
@@ -115,6 +115,7 @@ int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
 int masked_imma_prepare(gplvm_ppca_session* s, ShardState& sh);
 int masked_imma_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
+double* masked_imma_guard_scal(ShardState& sh);
 int masked_dmma_s2(gplvm_ppca_session* s, ShardState& sh, const double* ez, int64_t ldez, double* dst);
 int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
 // masked.cu
@@ -126,7 +127,7 @@ int masked_restore(gplvm_ppca_session* s, double* restored, int64_t ld);
 int session_allreduce_stats(gplvm_ppca_session* s, size_t count);
 int session_setup_p2p(gplvm_ppca_session* s);
 void session_release_p2p(gplvm_ppca_session* s);
-int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst = nullptr);
+int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst = nullptr, double* scal = nullptr);  // scal: S_DONE skip flag block, default the session's
 
 // Generic split-K statistics GEMM shared by dense.cu and masked.cu (defined in dense.cu).
 // out block 1: rows [0,R1) x Q1 columns, block 2: rows [R1,R) x Q2 columns (Q2 <= Q1).

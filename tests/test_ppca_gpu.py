@@ -210,6 +210,20 @@ def test_missing_steps_vs_oracle_synthetic(d, n, m, p):
         assert rel(restored, ref.restored_matrix) < TOL_RESTORED
 
 
+def test_missing_outlier_observation_takes_fp64_fallback():
+    """One observation 2000x larger than the rest puts > 1 % of the [vech A | ez] entries more than 2^20 below the
+    class maximum: the precision guard of the INT8 complement sums (masked_imma.cu) must hand this step to the FP64
+    DMMA product on the device.  Tolerances are looser: tot - miss_d cancels ~7 digits with such an outlier."""
+    Y, W0 = synth(256, 2048, 16, seed=99, nan_prob=0.2)
+    Y[:, 5] *= 2000.0
+    ref = oppca.em_steps_missed_vectorised(Y, W0, 1.0, ("left", 2))
+    W, s2, ll, restored = g.em_steps_missed(Y, W0, 1.0, g.Left(2))
+    assert rel(W, ref.W) < 1e-6, rel(W, ref.W)
+    assert abs(s2 - ref.variance) < 1e-7 * ref.variance
+    assert abs(ll - ref.final_exp_likelihood) < 1e-7 * abs(ref.final_exp_likelihood)
+    assert rel(restored, ref.restored_matrix) < 1e-6
+
+
 def test_missing_literal_oracle_small():
     """Against the LITERAL per-observation closures of the reference (slow; small case)."""
     Y, W0 = synth(12, 60, 3, seed=3, nan_prob=0.25)
