@@ -321,10 +321,14 @@ def main():
     total_ms, _ = sess.last_steps_ms()
     # nvidia-smi samples every 100 ms; when the timed region is shorter than a few samples keep the SAME load running
     # (untimed) until the clock record has at least 3 samples under load
+    # (the ranks must agree on the number of extra steps -- every step carries a collective -- so the decision is a MAX
+    # over ranks; the extra steps are reported as part of "em_steps_total", which is what sigma2 / loglik correspond to)
     t_extra = time.perf_counter()
-    while len(sampler.lines) < 3 and time.perf_counter() - t_extra < 2.0:
+    extra_steps = 0
+    while max_over_ranks(1.0 if (len(sampler.lines) < 3 and time.perf_counter() - t_extra < 2.0) else 0.0) > 0.0:
         sess.steps(args.steps)
         sess.sync()
+        extra_steps += args.steps
     clocks = sampler.stop()
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
@@ -432,7 +436,8 @@ def main():
                            "l2": "inputs (%.1f GB per rank) exceed the 126 MB L2; no flush" % (8 * D * count / 1e9),
                            "init": "W0 ~ N(0,1) seed 4321, sigma2_0 = 1"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "sigma2": p["sigma2"], "loglik": ll}
+                "cpu_baseline": cpu_baseline, "sigma2": p["sigma2"], "loglik": ll,
+                "em_steps_total": args.warmup + args.steps + extra_steps + min(args.steps, 10)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         lib.gplvm_dist_finalize()
