@@ -566,7 +566,7 @@ int masked_init_constants(gplvm_ppca_session* s) {
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     GP_LAUNCH(masked_bits_kernel, (unsigned)ceil_div(sh.n, 8), 256, 0, sh.st, sh.X, sh.ldx, sh.n, (int)s->D, s->WPR, sh.mbits);
-    if (sh.mbitsT) GP_TRY(masked_imma_prepare(s, sh));
+    if (sh.mbitsT) GP_TRY(masked_use_legacy_imma() ? masked_imma_prepare(s, sh) : masked_utc_prepare(s, sh));
   }
   GP_TRY(moments_pass(s, 2));
   GP_TRY(session_allreduce_stats(s, 3 * s->D));

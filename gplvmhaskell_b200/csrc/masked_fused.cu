@@ -432,7 +432,8 @@ int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc
 
 // complement sums [G^miss | S1^miss] (D x 152) + totals (152) into dst (length (D + 1) x 152)
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
-  // default: exact fixed-point sums on the INT8 tensor cores (masked_imma.cu), followed by the FP64 DMMA product as a
+  // default: exact fixed-point sums on the INT8 tensor cores (tcgen05: masked_utc.cu; legacy mma.sync with
+  // GPLVM_MISS_IMMA=1: masked_imma.cu), followed by the FP64 DMMA product as a
   // device-side fallback that runs only when the precision guard of the INT8 path fired (its `scal` block is the guard's:
   // S_DONE = 1.0 makes both kernels return at once).  GPLVM_MISS_DMMA=1 selects the FP64 product unconditionally.
   static const bool force_dmma = []() {
@@ -440,7 +441,7 @@ int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
     return e ? (atoi(e) != 0) : false;
   }();
   const bool imma = !force_dmma && sh.mbitsT;
-  if (imma) GP_TRY(masked_imma_miss_sums(s, sh, dst));
+  if (imma) GP_TRY(masked_use_legacy_imma() ? masked_imma_miss_sums(s, sh, dst) : masked_utc_miss_sums(s, sh, dst));
   double* scal = imma ? masked_imma_guard_scal(sh) : sh.par.scal;
   const int64_t Spart = (int64_t)(s->D + 1) * EASF;
   const int fgroups = (int)std::max<int64_t>(1, s->D / 128);
@@ -455,6 +456,14 @@ int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
   }
   GP_TRY(rc);
   return launch_reduce_partials(sh, Spart, rb, dst, scal);
+}
+
+bool masked_use_legacy_imma() {
+  static const bool legacy = []() {
+    const char* e = getenv("GPLVM_MISS_IMMA");
+    return e ? (atoi(e) != 0) : false;
+  }();
+  return legacy;
 }
 
 }  // namespace gplvm

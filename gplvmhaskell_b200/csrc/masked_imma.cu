@@ -21,19 +21,17 @@
 // then 4 k32 steps of 2 x NT IMMAs per warp (8 warps x 32 features).  Tiles are double buffered: one barrier per chunk.
 // The totals row (sum over ALL observations) is accumulated by the cutting threads as integer sums of the two halves
 // of u.  A small finalize kernel adds the splits in int64, assembles the 128-bit integers and rounds once.
+#include "masked_fx.cuh"
 #include "ppca.cuh"
 #include "tma.cuh"
 
 namespace gplvm {
 namespace {
 
-constexpr int NSL = 7;              // byte planes of the 52-bit fixed-point value
-constexpr int FXP = 51;             // |x| < 2^FXP
-constexpr int IM_CHUNK = 128;       // observations per shared-memory tile
+using namespace fx;
+
 constexpr int IM_PITCH = 160;       // bytes per tile row (128 + 32: rows 4 apart in g land in different bank groups)
 constexpr int IM_LDP = 72;          // int32 columns per feature row in the per-CTA partial block
-constexpr int IM_EAS = 152;
-constexpr int IM_NV = 136;
 constexpr int IM_PF = 3;            // cp.async stages of the entries (prefetch distance: 2 chunks)
 constexpr int IM_STAGE_BYTES = (256 + 64) * 32;
 constexpr int IM_MS = 4;            // stages of the mask words (DD x 16 B each)
@@ -44,32 +42,6 @@ __device__ __forceinline__ void imma_s8u8(int (&c)[4], const uint32_t (&a)[4], u
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// biased exponent of the class maximum, clamped so that both 2^(51 - E) and 2^(E - 51) are normal numbers
-__device__ __forceinline__ int class_exponent(uint32_t hmax) {
-  int ex = (int)((hmax >> 20) & 0x7ffu);
-  return min(max(ex, 60), 2040);
-}
-__device__ __forceinline__ double scale_up(uint32_t hmax) {      // 2^(FXP - E),  E = ex - 1022
-  return __hiloint2double((1023 + FXP + 1022 - class_exponent(hmax)) << 20, 0);
-}
-__device__ __forceinline__ double scale_down(uint32_t hmax) {    // 2^(E - FXP)
-  return __hiloint2double((1023 - FXP - 1022 + class_exponent(hmax)) << 20, 0);
-}
-
-// eamax block (256 B, device): [0] / [1] high words of max |vech A| / max |ez| (solver), then two 64-bit counters of
-// entries that the fixed-point grid resolves poorly, then S_COUNT doubles used as the `scal` block of the FP64 fallback
-// kernels (slot S_DONE = 1.0: skip, the INT8 result stands).
-constexpr int IM_GUARD_BITS = 20;
-__host__ __device__ inline unsigned long long* guard_counts(uint32_t* eamax) { return reinterpret_cast<unsigned long long*>(eamax + 2); }
-__host__ __device__ inline double* guard_scal(uint32_t* eamax) { return reinterpret_cast<double*>(eamax + 16); }
-// more than 1 % of the entries of a class more than 2^20 below its maximum (an outlier sets the scale): the grid would
-// leave typical entries fewer than 32 bits, so this step's sums are redone in FP64 (masked_miss_dmma_kernel)
-__device__ __forceinline__ bool guard_fallback(const uint32_t* eamax, int64_t n_obs) {
-  const unsigned long long* cnt = reinterpret_cast<const unsigned long long*>(eamax + 2);
-  // the counters sample one observation in four
-  return cnt[0] * 400ull > (unsigned long long)n_obs * IM_NV || cnt[1] * 400ull > (unsigned long long)n_obs * (IM_EAS - IM_NV);
-}
-
 // cuts 4 consecutive observations of one column into byte planes and stores plane s as one 32-bit word
 __device__ __forceinline__ void cut_store(const double (&v)[4], double sc, uint32_t thr, int64_t o0, int64_t n_obs, uint32_t dst,
                                           unsigned long long& tlo, unsigned long long& thi, uint32_t& small) {
@@ -367,10 +339,7 @@ __global__ void __launch_bounds__(256) masked_miss_imma_finalize(const int* __re
     }
     T = ((__int128)hi << 32) + (__int128)lo - ((__int128)n_obs << FXP);
   }
-  // |T| < 2^(51 + 24): the upper part is exact in FP64, one fused rounding when the low 24 bits are added
-  const long long thi = (long long)(T >> 24), tlo = (long long)(T & 0xffffff);
-  const double r = fma((double)thi, 16777216.0, (double)tlo);
-  dst[idx] = r * scale_down((c < IM_NV) ? eamax[0] : eamax[1]);
+  dst[idx] = int128_to_double(T) * scale_down((c < IM_NV) ? eamax[0] : eamax[1]);
 }
 
 // Transposed copy of the mask bits in MMA-fragment order (constant over the EM iterations): one contiguous D x 16 B

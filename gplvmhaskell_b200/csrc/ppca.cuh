@@ -116,6 +116,9 @@ int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
 int masked_imma_prepare(gplvm_ppca_session* s, ShardState& sh);
 int masked_imma_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
 double* masked_imma_guard_scal(ShardState& sh);
+int masked_utc_prepare(gplvm_ppca_session* s, ShardState& sh);
+int masked_utc_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
+bool masked_use_legacy_imma();   // GPLVM_MISS_IMMA=1: mma.sync IMMA kernel instead of the tcgen05 one
 int masked_dmma_s2(gplvm_ppca_session* s, ShardState& sh, const double* ez, int64_t ldez, double* dst);
 int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
 // masked.cu
