@@ -11,7 +11,7 @@
 // write; tools/tcgen05_i8_check.cu pins it), then fence.proxy.async + arrive on full[buffer].  Warp 8 lane 0 is the MMA
 // ISSUER: waits full[b], issues (D / 128) x 4 MMAs (K = 32 each, the K offset goes into the descriptor start address),
 // and tcgen05.commit's to empty[b], which the producers wait on before they overwrite the buffer.  Two operand
-// buffers; entries and mask words are staged 2 chunks ahead by per-thread cp.async (as in masked_imma.cu).  After the
+// buffers; entries (flattened, coalesced) and mask words are staged 2 chunks ahead by cp.async.  After the
 // last chunk warps 0..3 read the accumulators with tcgen05.ld (warp w owns TMEM lanes 32 w ..) and store the per-CTA
 // int32 block; the finalize kernel adds the splits in int64, assembles 128-bit integers and rounds once.
 // Every wait is bounded (a failed handshake raises S_ERR instead of hanging the GPU).
@@ -32,7 +32,7 @@ constexpr int UT_PROD = 256;                 // producer threads
 constexpr int UT_THREADS = UT_PROD + 32;
 constexpr int UT_TASKS = 3;                  // (column quad, quad block) tasks per producer thread: 5 x 4 = 20 over 8 warps
 constexpr int UT_B_BYTES = UT_N * 128;       // 18 432
-constexpr int UT_STAGE_BYTES = UT_TASKS * UT_PROD * 32;   // private entry slots: [task][row r][thread] x 8 B
+constexpr int UT_STAGE_BYTES = IM_CHUNK * UT_NC * 8;        // staged entries of a chunk: [128 observations][19 columns] FP64
 constexpr int UT_PF = 3;                     // cp.async stages (prefetch distance 2)
 constexpr long long UT_SPIN = 1ll << 26;
 static_assert(UT_GROUPS * UT_NC == IM_EAS, "column groups");
@@ -150,50 +150,55 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
     }
   } else {
     // ---------------------------------------------------------------- producers --------------------------------------
-    // task j of warp w: id = w + 8 j < 20 -> column quad id >> 2 (columns 4 cq + (lane & 3)), quad block id & 3
-    // (observation quads 8 kb + (lane >> 2)): per load instruction a warp touches 8 rows x 32 contiguous bytes
+    // Cutting task j of warp w: id = w + 8 j < 20 -> column quad cq = id >> 2, quad block kb = id & 3 (observation quads
+    // 8 kb + (lane >> 2)).  A column quad takes every second column (cq < 4: 8 (cq >> 1) + (cq & 1) + 2 (lane & 3); cq = 4:
+    // 16 + (lane & 3)): rows 7 c + s of columns two apart differ by 6 mod 8, so the 4 x 8 plane words of a store
+    // instruction fall into 32 different banks of the swizzled tile.
     int tcol[UT_TASKS], tkq[UT_TASKS];
     bool tval[UT_TASKS];
     double tsc[UT_TASKS];
-    uint32_t tthr[UT_TASKS], tdst[UT_TASKS];
+    uint32_t tthr[UT_TASKS];
     const uint32_t hA = eamax[0], hE = eamax[1];
 #pragma unroll
     for (int j = 0; j < UT_TASKS; ++j) {
-      const int id = w + 8 * j;
-      tcol[j] = 4 * (id >> 2) + (lane & 3);
+      const int id = w + 8 * j, cq = id >> 2;
+      tcol[j] = (cq < 4) ? 8 * (cq >> 1) + (cq & 1) + 2 * (lane & 3) : 16 + (lane & 3);
       tkq[j] = 8 * (id & 3) + (lane >> 2);
       tval[j] = id < 20 && tcol[j] < UT_NC;
       const bool isA = col0 + tcol[j] < IM_NV;
       tsc[j] = scale_up(isA ? hA : hE);
       tthr[j] = (uint32_t)(class_exponent(isA ? hA : hE) - IM_GUARD_BITS) << 20;
-      tdst[j] = 0;   // row 7 c + s, bytes 4 kq .. 4 kq + 3: filled per plane below
     }
     unsigned long long tlo[UT_TASKS], thi[UT_TASKS];
     uint32_t small[UT_TASKS];
 #pragma unroll
     for (int j = 0; j < UT_TASKS; ++j) tlo[j] = thi[j] = 0ull, small[j] = 0u;
 
-    const double* pe[UT_TASKS];
-#pragma unroll
-    for (int j = 0; j < UT_TASKS; ++j) pe[j] = EA + (chunk_begin * IM_CHUNK + 4 * tkq[j]) * IM_EAS + col0 + (tval[j] ? tcol[j] : 0);
+    // Staging: the 128 x 19 entries of a chunk are copied element-wise (8-byte cp.async) in flattened order, thread t
+    // taking elements t, t + 256, ...: a warp instruction reads 32 consecutive entries (at most 3 rows of the column
+    // group) and writes 256 contiguous bytes.  Mask words: thread t copies the 16 bytes of feature t.
+    const int er0 = tid / UT_NC, ec0 = tid % UT_NC;   // element tid = (row er0, column ec0); + 256 = (+ 13 rows, + 9 columns)
+    const double* pe = EA + chunk_begin * IM_CHUNK * IM_EAS + col0;
     const uint32_t* pm = mT + (chunk_begin * DD + (tid % DD)) * 4;
     int pf_stage = 0;
     int64_t pf_chunk = chunk_begin;
     auto prefetch = [&]() {
       if (pf_chunk < chunk_end) {
         const uint32_t st = stage_u + (uint32_t)pf_stage * UT_STAGE_BYTES;
+        int er = er0, ec = ec0;
 #pragma unroll
-        for (int j = 0; j < UT_TASKS; ++j)
-          if (tval[j]) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + (uint32_t)(((j * 4 + r) * UT_PROD + tid) * 8)),
-                           "l"(pe[j] + r * IM_EAS)
-                           : "memory");
-            pe[j] += IM_CHUNK * IM_EAS;
-          }
+        for (int m = 0; m < (IM_CHUNK * UT_NC + UT_PROD - 1) / UT_PROD; ++m) {
+          if (tid + UT_PROD * m < IM_CHUNK * UT_NC)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + (uint32_t)((tid + UT_PROD * m) * 8)),
+                         "l"(pe + er * IM_EAS + ec)
+                         : "memory");
+          er += 13;
+          ec += 9;
+          if (ec >= UT_NC) ec -= UT_NC, ++er;
+        }
         if (tid < DD)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mask_u + (uint32_t)(pf_stage * DD * 16 + tid * 16)), "l"(pm) : "memory");
+        pe += IM_CHUNK * IM_EAS;
         pm += DD * 4;
         pf_stage = (pf_stage + 1 == UT_PF) ? 0 : pf_stage + 1;
         ++pf_chunk;
@@ -207,8 +212,9 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
     for (int64_t i = 0; i < my_chunks; ++i) {
       const int b = (int)(i & 1);
       const int64_t chunk = chunk_begin + i;
-      prefetch();
-      asm volatile("cp.async.wait_group 2;" ::: "memory");   // this thread's entries and mask words of `chunk` have landed
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of `chunk` have landed
+      asm volatile("bar.sync 1, 256;" ::: "memory");         // ... and everybody's; all producers are done cutting chunk - 1,
+      prefetch();                                            // whose stage is the one this prefetch (chunk + 2) overwrites
       if (i >= 2 && ok) ok = mbar_wait_bounded(bar_u + 16 + 8 * b, (uint32_t)(((i >> 1) - 1) & 1));   // MMAs of chunk i - 2 released the buffer
       uint8_t* Abuf = base + b * C::BUF_BYTES;
       const uint32_t b_u = base_u + b * C::BUF_BYTES + C::A_BYTES;
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
           double v0 = 0.0;
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            const double v = lds64(st + (uint32_t)(((j * 4 + r) * UT_PROD + tid) * 8));
+            const double v = lds64(st + (uint32_t)(((4 * tkq[j] + r) * UT_NC + tcol[j]) * 8));
             if (r == 0) v0 = v;
             const double y = fma(v, tsc[j], 6755399441055744.0);   // 2^52 + 2^51: the mantissa of y is the integer x + 2^51
             lo[r] = (uint32_t)__double2loint(y);
@@ -273,7 +279,6 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_u + 8 * b) : "memory");
     }
     if (!ok) set_err(scal, 3.0);
-    (void)tdst;
     // ---- precision-guard counters and totals (integer sums: order-independent) -----------------------------------------
     uint32_t sA = 0u, sE = 0u;
 #pragma unroll
@@ -303,13 +308,14 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
   }
   // ------------------------------------------------------------------ epilogue ---------------------------------------
   __syncthreads();
-  if (tid < 2 * UT_NC) {   // column c: tasks id = 4 (c >> 2) + kb, kb = 0..3 -> (warp id & 7, slot id >> 3)
+  if (tid < 2 * UT_NC) {   // column c lives in column quad cq, lane slot cl; tasks id = 4 cq + kb -> (warp id & 7, slot id >> 3)
     const int c = tid >> 1, h = tid & 1;
+    const int cq = (c < 16) ? 2 * (c >> 3) + (c & 1) : 4, cl = (c < 16) ? (c & 7) >> 1 : c - 16;
     unsigned long long a = 0ull;
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
-      const int id = 4 * (c >> 2) + kb;
-      a += tred[(((id & 7) * UT_TASKS + (id >> 3)) * 4 + (c & 3)) * 2 + h];
+      const int id = 4 * cq + kb;
+      a += tred[(((id & 7) * UT_TASKS + (id >> 3)) * 4 + cl) * 2 + h];
     }
     tp[tid] = a;
   }
