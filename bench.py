@@ -360,7 +360,7 @@ def main():
     # 7.59 GB over the four masked kernels for 2^20 observations), scaled to this rank's observation count
     traffic = (7.59e9 / (1 << 20) if missing else (17.180e9 + 4.4e6) / (1 << 23)) * count
     roofline = {"bound": "tensor", "achieved": ach_tf, "peak": dmma.value, "unit": "TFLOP/s", "frac": ach_tf / dmma.value,
-                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum (profiles/), per launch", "kernel": ("masked E-step + statistics (TMA/DMMA b pass, register solver, exact INT8 fixed-point complement sums (IMMA), DMMA S2 pass) per rank; FP64-equivalent algorithmic flops against the DMMA peak"
+                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum (profiles/), per launch", "kernel": ("masked E-step + statistics (TMA/DMMA b pass, register solver, exact INT8 fixed-point complement sums (tcgen05 kind::i8), DMMA S2 pass) per rank; FP64-equivalent algorithmic flops against the DMMA peak"
                            if missing else "dense statistics pass (X.A, X^T.Ez, Ez^T.Ez) per rank"),
                 "kernel_ms": k_ms, "peak_source": "in-run DMMA.8x8x4 register-chain probe (no FP64 entry in MEASURED_PEAKS.json); "
                 "cublasDgemm 8192^3 measured 35.8 TFLOP/s (profiles/r1_fp64_peaks.log)",
