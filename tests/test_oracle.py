@@ -152,3 +152,76 @@ def test_masked_em_without_nan_reaches_the_dense_fixed_point(iris):
     assert abs(a.variance - b.variance) < 1e-7 * a.variance
     assert np.max(np.abs(oppca.projector(a.W) - oppca.projector(b.W))) < 1e-6
     assert np.max(np.abs(b.restored_matrix - Y)) < 1.0   # the restored matrix is the rank-3 reconstruction (+ mean)
+
+
+# ---------------------------------------------------------------------------------------------------
+# exact fixed-point arithmetic of the INT8 complement sums (oracle/fixedpoint.py restates the device arithmetic)
+# ---------------------------------------------------------------------------------------------------
+
+def _fx_case(seed, n=4000, outlier=None):
+    import oracle.fixedpoint as fx
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(n) * rng.choice([1e-3, 1.0, 37.5], n)
+    if outlier:
+        v[17] = outlier
+    mask = rng.random(n) < 0.2
+    hmax = max(fx.hi_word_abs(x) for x in v)
+    return fx, v, mask, hmax
+
+
+def test_fixed_point_sum_is_the_exact_sum_of_the_rounded_entries():
+    from fractions import Fraction
+    fx, v, mask, hmax = _fx_case(1)
+    u = fx.to_fixed(v, hmax)
+    assert int(u.max()) <= 2 ** 52 and int(u.min()) >= 0
+    x = [int(a) - 2 ** 51 for a in u]                                   # the rounded fixed-point entries
+    # each entry is within half a grid step of v * scale
+    sc = Fraction(fx.scale_up(hmax))
+    assert all(abs(Fraction(float(a)) * sc - b) <= Fraction(1, 2) for a, b in zip(v, x))
+    exact = sum(b for b, m in zip(x, mask) if m)
+    got = fx.masked_sum(v, mask, hmax)
+    assert got == float(Fraction(exact) * Fraction(fx.scale_down(hmax)))   # one rounding of the exact integer sum
+
+
+def test_fixed_point_sum_is_independent_of_the_split_and_close_to_fsum():
+    import math
+    fx, v, mask, hmax = _fx_case(2)
+    ref = math.fsum(v[mask])
+    sums = {fx.masked_sum(v, mask, hmax, splits=s) for s in (1, 2, 7, 18, 37)}
+    assert len(sums) == 1                                                # bitwise identical for every split
+    got = sums.pop()
+    bound = mask.sum() * 2.0 ** (fx.class_exponent(hmax) - 1022 - 52)    # count x half a grid step
+    assert abs(got - ref) <= bound + abs(ref) * 2.0 ** -52
+
+
+def test_fixed_point_grid_is_set_by_the_class_maximum():
+    """An outlier coarsens the grid of every other entry: this is what the device-side precision guard watches."""
+    import math
+    fx, v, mask, hmax = _fx_case(3, outlier=1e9)
+    mask[17] = False
+    ref = math.fsum(v[mask])
+    got = fx.masked_sum(v, mask, hmax)
+    step = 2.0 ** (fx.class_exponent(hmax) - 1022 - 51)
+    assert step > 1e-7                                                   # the grid is coarse ...
+    assert abs(got - ref) <= mask.sum() * step / 2                       # ... but the sum of the rounded entries is still exact
+
+
+def test_mask_bit_layouts_expand_to_mask_bytes():
+    import oracle.fixedpoint as fx
+    rng = np.random.default_rng(4)
+    std = [int(x) for x in rng.integers(0, 2 ** 32, 4, dtype=np.uint64)]   # bit i of word w = observation 32 w + i
+    bits = [(std[o >> 5] >> (o & 31)) & 1 for o in range(128)]
+    # tcgen05 kernel: (W >> s) & 0x01010101 = mask bytes of observations 32 wq + 4 s .. + 3
+    for wq in range(4):
+        W = fx.expand_order_word(std[wq])
+        for s in range(8):
+            word = (W >> s) & 0x01010101
+            assert [(word >> (8 * b)) & 0xFF for b in range(4)] == bits[32 * wq + 4 * s: 32 * wq + 4 * s + 4]
+    # mma.sync kernel: (W_t >> (2 ks + h)) & 0x01010101 = A-fragment register (k = 16 h + 4 t .. + 3 of k32 step ks)
+    Wt = fx.fragment_order_words(std)
+    for t in range(4):
+        for ks in range(4):
+            for h in range(2):
+                word = (Wt[t] >> (2 * ks + h)) & 0x01010101
+                k0 = 32 * ks + 16 * h + 4 * t
+                assert [(word >> (8 * b)) & 0xFF for b in range(4)] == bits[k0: k0 + 4]
