@@ -1,5 +1,7 @@
 // masked_imma.cu -- complement sums of the NaN-masked M-step as an EXACT fixed-point product on the INT8 tensor
 // cores (mma.sync.m16n8k32.s8.u8 -> s32; 1.14 POP/s on B200, tools/imma_peak.cu, against 37 TFLOP/s of DMMA).
+// This is the legacy-path kernel (GPLVM_MISS_IMMA=1); the default is the tcgen05 kernel of masked_utc.cu, which
+// computes the same integers.  The derivation below holds for both; oracle/fixedpoint.py restates it on the CPU.
 //
 //   miss (D x 152) = Miss^T (D x n) . [vech A | ez] (n x 152),   Miss[i][d] = 1 when observation i misses feature d
 // (reference: the per-feature sums over the observations that miss / have the feature, emStepsMissed.stepTwo,
@@ -21,6 +23,8 @@
 // then 4 k32 steps of 2 x NT IMMAs per warp (8 warps x 32 features).  Tiles are double buffered: one barrier per chunk.
 // The totals row (sum over ALL observations) is accumulated by the cutting threads as integer sums of the two halves
 // of u.  A small finalize kernel adds the splits in int64, assembles the 128-bit integers and rounds once.
+// Precision guard: the cutting threads count (sampled) the entries more than 2^20 below their class maximum; above 1 %
+// the finalize kernel hands the step to the FP64 product of masked_fused.cu on the device (masked_fx.cuh).
 #include "masked_fx.cuh"
 #include "ppca.cuh"
 #include "tma.cuh"
