@@ -98,3 +98,65 @@ def fragment_order_words(std_words: list[int]) -> list[int]:
                     o |= ((std_words[ks] >> (16 * h + 4 * t + b)) & 1) << (8 * b + 2 * ks + h)
         out.append(o)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Numerical design of the NEXT step: FP64-faithful dense statistics with BOTH factors in byte planes
+# (Ozaki splitting) -- emulated exactly with integers; tools/dense_i8_proto.cu measures step 1 of it on tcgen05.
+# ---------------------------------------------------------------------------------------------------------------------
+
+def balanced_planes(xi: np.ndarray, n: int) -> list[np.ndarray]:
+    """Balanced base-256 digits (each in [-128, 127]) of an int64 array, least significant first."""
+    out, x = [], xi.astype(np.int64).copy()
+    for _ in range(n):
+        lo = ((x & 0xFF) ^ 0x80) - 0x80          # sign-extended low byte
+        out.append(lo)
+        x = (x - lo) >> 8
+    assert np.all(x == 0), "digits overflow"
+    return out
+
+
+def pair_product(Ap: list[np.ndarray], Bp: list[np.ndarray], top_keep: int) -> np.ndarray:
+    """sum over plane pairs of 256^(p+q) Ap[p] @ Bp[q], keeping the `top_keep` most significant weight classes p + q
+    (what accumulates in one group of s32 TMEM columns per class).  Exact: returns an object array of Python integers."""
+    P, Q = len(Ap), len(Bp)
+    top = P + Q - 2
+    acc = None
+    for w in range(top - top_keep + 1, top + 1):
+        cls = np.zeros((Ap[0].shape[0], Bp[0].shape[1]), dtype=np.int64)
+        for p in range(P):
+            q = w - p
+            if 0 <= q < Q:
+                cls += Ap[p] @ Bp[q]
+        assert np.max(np.abs(cls)) < 2 ** 62
+        term = cls.astype(object) * (256 ** w)
+        acc = term if acc is None else acc + term
+    return acc
+
+
+def _to_float(obj: np.ndarray) -> np.ndarray:
+    return np.array([[float(v) for v in row] for row in obj], dtype=np.float64)   # one rounding per entry
+
+
+def dense_stats_i8(Xc: np.ndarray, W: np.ndarray, sigma2: float, cache: dict) -> np.ndarray:
+    """Same packed statistics as oracle.ppca.dense_stats ([XEz | Ez Ez^T]; Xc is D x N), formed the planned device way:
+    X' = Xc / c_f (feature maxima folded into the projector) cut ONCE into 7 planes; projector A' = c_f W M^-1 cut per
+    step with one scale per latent column; Ez cut into 8 planes with the a-priori bound max_i |x'_i| |A'_a|; every
+    product keeps its 7 most significant weight classes."""
+    from . import ppca as op
+    if "Xp" not in cache:
+        c = np.max(np.abs(Xc), axis=1)
+        c[c == 0] = 1.0
+        xi = np.rint(Xc / c[:, None] * 2.0 ** 54).astype(np.int64)
+        cache.update(c=c, Xp=balanced_planes(xi, 7), rown=float(np.sqrt(np.max(np.sum((Xc / c[:, None]) ** 2, axis=0)))))
+    c, Xp = cache["c"], cache["Xp"]
+    inv_m = np.linalg.inv(op.map_diagonal_add(W.T @ W, sigma2))
+    A = (W @ inv_m) * c[:, None]
+    sa = np.max(np.abs(A), axis=0)
+    Apl = balanced_planes(np.rint(A / sa * 2.0 ** 54).astype(np.int64), 7)
+    ez = _to_float(pair_product([x.T for x in Xp], Apl, 7)) * 2.0 ** -108 * sa            # N x M
+    se = cache["rown"] * np.sqrt(np.sum(A ** 2, axis=0))                                # |Ez_a| <= |x'| |A'_a|
+    Epl = balanced_planes(np.rint(ez / se * 2.0 ** 62).astype(np.int64), 8)
+    xez = _to_float(pair_product(Xp, Epl, 7)) * 2.0 ** -(54 + 62) * c[:, None] * se[None, :]
+    ee = _to_float(pair_product([e.T for e in Epl], Epl, 7)) * 2.0 ** -124 * se[:, None] * se[None, :]
+    return np.concatenate([xez.ravel(), ee.ravel()])
