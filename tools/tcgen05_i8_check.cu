@@ -17,7 +17,9 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
 // byte (row r, k-byte b) of a K-major tile with 128-byte rows, 8-row groups of 1024 B, 16-byte units XOR-swizzled by r & 7
 __host__ __device__ inline uint32_t sw128(int r, int b) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((b >> 4) ^ (r & 7))) << 4) + (b & 15)); }
 
-__global__ void __launch_bounds__(128, 1) check(const int8_t* __restrict__ Ag, const uint8_t* __restrict__ Bg, int* __restrict__ Dg, int* err) {
+// a_mn = 1: the SAME A tile is read MN-major (instruction-descriptor bit 15): D[m][n] = sum_k A[k][m] B[n][k], i.e. the
+// tile is used transposed -- what X^T . Ez needs.  K then advances by 32 ROWS (4096 B) per MMA.
+__global__ void __launch_bounds__(128, 1) check(const int8_t* __restrict__ Ag, const uint8_t* __restrict__ Bg, int* __restrict__ Dg, int* err, int a_mn) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base;
   __shared__ __align__(8) unsigned long long bar;
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(128, 1) check(const int8_t* __restrict__ Ag, c
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base;
   // D = S32, A signed 8 bit, B unsigned 8 bit, both K-major
-  const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(a_mn ? 1u : 0u) << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
   const uint64_t adesc = smem_desc_sw128(smem_u32(A)), bdesc = smem_desc_sw128(smem_u32(B));
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(128, 1) check(const int8_t* __restrict__ Ag, c
       asm volatile(
           "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
           "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem),
-          "l"(adesc + 2 * k), "l"(bdesc + 2 * k), "r"(idesc), "r"(acc), "r"(0u)
+          "l"(adesc + (a_mn ? 256 * k : 2 * k)), "l"(bdesc + 2 * k), "r"(idesc), "r"(acc), "r"(0u)
           : "memory");
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u) : "memory");
@@ -101,23 +103,29 @@ int main() {
   cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice);
   const int smem = (M + N) * 128 + 1024;
   cudaFuncSetAttribute(check, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  check<<<1, 128, smem>>>(dA, dB, dD, derr);
-  cudaError_t rc = cudaDeviceSynchronize();
-  std::vector<int> D(M * N);
-  int herr = 0;
-  cudaMemcpy(D.data(), dD, sizeof(int) * M * N, cudaMemcpyDeviceToHost);
-  cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost);
-  long bad = 0;
-  for (int m = 0; m < M; ++m)
-    for (int n = 0; n < N; ++n) {
-      int ref = 0;
-      for (int k = 0; k < K; ++k) ref += (int)A[m * K + k] * (int)B[n * K + k];
-      if (ref != D[m * N + n]) {
-        if (bad < 5) printf("mismatch D[%d][%d] = %d, expected %d\n", m, n, D[m * N + n], ref);
-        ++bad;
+  int fails = 0;
+  for (int a_mn = 0; a_mn < 2; ++a_mn) {
+    cudaMemset(dD, 0xff, sizeof(int) * M * N);
+    check<<<1, 128, smem>>>(dA, dB, dD, derr, a_mn);
+    cudaError_t rc = cudaDeviceSynchronize();
+    std::vector<int> D(M * N);
+    int herr = 0;
+    cudaMemcpy(D.data(), dD, sizeof(int) * M * N, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost);
+    long bad = 0;
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < N; ++n) {
+        int ref = 0;
+        for (int k = 0; k < K; ++k) ref += (int)(a_mn ? A[k * K + m] : A[m * K + k]) * (int)B[n * K + k];
+        if (ref != D[m * N + n]) {
+          if (bad < 3) printf("mismatch D[%d][%d] = %d, expected %d\n", m, n, D[m * N + n], ref);
+          ++bad;
+        }
       }
-    }
-  printf("tcgen05 kind::i8 s8 x u8 known-answer check: %s, timeout flag %d, %ld mismatches of %d -> %s\n", cudaGetErrorString(rc), herr, bad,
-         M * N, (rc == cudaSuccess && !herr && bad == 0) ? "PASS" : "FAIL");
-  return (rc == cudaSuccess && !herr && bad == 0) ? 0 : 1;
+    const bool pass = rc == cudaSuccess && !herr && bad == 0;
+    printf("tcgen05 kind::i8 s8 x u8 known-answer check, A %s: %s, timeout flag %d, %ld mismatches of %d -> %s\n",
+           a_mn ? "MN-major (tile used transposed)" : "K-major", cudaGetErrorString(rc), herr, bad, M * N, pass ? "PASS" : "FAIL");
+    fails += pass ? 0 : 1;
+  }
+  return fails;
 }
