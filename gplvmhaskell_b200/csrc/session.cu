@@ -216,7 +216,7 @@ static int check_async(gplvm_ppca_session* s, double* scal_out) {
     if (scal[S_ERR] == 2.0)
       return fail(GPLVM_ERR_UNSUPPORTED, "missing-data PPCA: an observation has every feature missing (unsupported by the reference, Util.hs:81)");
     if (scal[S_ERR] == 3.0)
-      return fail(GPLVM_ERR_NCCL, "peer statistics exchange timed out (a rank did not publish its statistics)");
+      return fail(GPLVM_ERR_NCCL, "a bounded device-side wait expired (peer statistics exchange: a rank did not publish its statistics; or the tcgen05 producer / MMA handshake of the masked complement sums)");
     if (scal[S_ERR] != 0.0)
       return fail(GPLVM_ERR_NUMERIC, "PPCA: a matrix that must be positive definite is not (step %lld)", (long long)scal[S_STEPS]);
     if (&sh == &s->sh[0] && scal_out) memcpy(scal_out, scal, sizeof scal);
