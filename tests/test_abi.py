@@ -111,3 +111,18 @@ def test_header_is_valid_c99_and_links(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "sm_100a" in r.stdout and "null" in r.stdout
+
+
+@pytest.mark.parametrize("src", ["imma_peak.cu", "tcgen05_i8_peak.cu", "tcgen05_i8_check.cu", "dense_i8_proto.cu", "dense_i8_proto2.cu"])
+def test_measurement_tools_compile_for_sm_100a(src, tmp_path):
+    """The INT8 probes / known-answer checks that DESIGN.md cites (profiles/r1_fp64_peaks.log) must keep compiling."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / (src + ".o")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-c", os.path.join(root, "tools", src), "-o", str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
