@@ -113,7 +113,7 @@ def test_header_is_valid_c99_and_links(tmp_path):
     assert "sm_100a" in r.stdout and "null" in r.stdout
 
 
-@pytest.mark.parametrize("src", ["imma_peak.cu", "tcgen05_i8_peak.cu", "tcgen05_i8_check.cu", "dense_i8_proto.cu", "dense_i8_proto2.cu"])
+@pytest.mark.parametrize("src", ["imma_peak.cu", "tcgen05_i8_peak.cu", "tcgen05_i8_check.cu", "dense_i8_proto.cu", "dense_i8_proto2.cu", "dense_i8_stream.cu"])
 def test_measurement_tools_compile_for_sm_100a(src, tmp_path):
     """The INT8 probes / known-answer checks that DESIGN.md cites (profiles/r1_fp64_peaks.log) must keep compiling."""
     import shutil
