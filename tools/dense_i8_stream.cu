@@ -1,4 +1,6 @@
-// dense_i8_stream.cu -- DRAFT, NOT YET RUN ON HARDWARE (written after the round-1 GPU budget was spent).
+// dense_i8_stream.cu -- DRAFT.  Run ONCE on a B200 with the last seconds of the round-1 GPU budget, 1 tile per CTA
+// (`./dense_i8_stream 1`): PASS (XEz within 1.0e-16, Ez^T Ez within 5.2e-16 of the reference, no handshake timeout).  The
+// multi-tile path (ring reuse, S1(t + 1) / S2(t) interleave, read-outs every 64 tiles) and the timing are NOT yet exercised.
 //
 // Streaming prototype of the kernel blueprint in DESIGN.md section 7 (FP64-faithful dense EM statistics on tcgen05
 // kind::i8): one persistent CTA per SM streams 128-observation tiles of pre-cut, pre-swizzled X planes from HBM and
@@ -35,7 +37,7 @@ constexpr int B1KB = NB1 * 128;            // one k-block of the projector plane
 constexpr int FLUSH = 64;                  // tiles between read-outs: 7 pairs x 128 x 2^14 x 64 < 2^31
 constexpr int EPI = 128;                   // epilogue threads (warps 0..3); warp 4 loads, warp 5 issues
 constexpr int THREADS = EPI + 64;
-constexpr long long SPIN = 1ll << 26;
+constexpr long long SPIN = 1ll << 20;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
