@@ -578,6 +578,11 @@ int dense_init_constants(gplvm_ppca_session* s) {
     }
     GP_TRY(dense_centre(s, -1.0));
     s->centred = true;
+    if (dense_i8_enabled() && s->use_dmma)
+      for (ShardState& sh : s->sh) {
+        CUDA_TRY(cudaSetDevice(sh.dev));
+        GP_TRY(dense_i8_prepare(s, sh));
+      }
     GP_TRY(launch_moments(s, 3));
     GP_TRY(session_allreduce_stats(s, s->D));
     for (ShardState& sh : s->sh) {
@@ -594,7 +599,8 @@ int dense_init_constants(gplvm_ppca_session* s) {
 }
 
 // statistics pass with projection matrix proj (D x MP): fills sh.stats (local sums)
-static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double* proj) {
+static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double* proj, bool em_step = false) {
+  if (em_step && sh.i8_planes) return dense_i8_stats(s, sh, proj);   // experimental, GPLVM_DENSE_I8=1 only
   if (s->use_dmma) return dense_dmma_stats(s, sh, proj);
   const int MP = s->MP, D = (int)s->D;
   const size_t smem = sizeof(double) * (64 * MP + 32 * 65);
@@ -617,7 +623,7 @@ int dense_enqueue_step(gplvm_ppca_session* s) {
       sh.peer_args.epoch = s->xchg_epoch;
       sh.peer_args.S = (long long)s->S;
     }
-    GP_TRY(dense_stats_pass(s, sh, sh.par.A));
+    GP_TRY(dense_stats_pass(s, sh, sh.par.A, true));
     sh.peer_args.peers = nullptr;
     if (sh.evk1) CUDA_TRY(cudaEventRecord(sh.evk1, sh.st));
   }

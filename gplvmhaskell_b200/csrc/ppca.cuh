@@ -65,6 +65,9 @@ struct ShardState {
   uint32_t* mbits = nullptr;   // masked: n x WPR words, bit d set = feature d of the observation is missing
   uint32_t* mbitsT = nullptr;  // masked fused path: D x nwT words, bit j of word w = observation 32 w + j misses the feature
   int64_t nwT = 0;             //   4 x ceil(n / 128) words per feature
+  uint8_t* i8_planes = nullptr;   // experimental INT8 dense statistics (dense_i8.cu, GPLVM_DENSE_I8=1): byte planes of Xc,
+  uint8_t* i8_aux = nullptr;      //   feature maxima / scales / projector planes,
+  long long* i8_scratch = nullptr;  //   per-CTA int64 class sums
   uint32_t* eamax = nullptr;   // masked fused path: 256 B block: class maxima of the last solve, precision-guard counters, guard flags (masked_imma.cu)
   double* parblock = nullptr;  // parameter block
   double* stats = nullptr;     // packed statistics (all-reduced), `S` doubles
@@ -110,6 +113,9 @@ bool dense_dmma_eligible(const gplvm_ppca_session* s);
 int dense_dmma_prepare(gplvm_ppca_session* s);
 int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int dense_dmma_release(gplvm_ppca_session* s);
+bool dense_i8_enabled();
+int dense_i8_prepare(gplvm_ppca_session* s, ShardState& sh);
+int dense_i8_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int masked_dmma_b(gplvm_ppca_session* s, ShardState& sh, const double* W, const double* mu, double* bout, double* yyout);
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out);
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);

@@ -86,7 +86,7 @@ int64_t chunk_obs(int64_t D) {
 
 void free_shard(ShardState& sh) {
   cudaSetDevice(sh.dev);
-  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.mbitsT); cudaFree(sh.eamax); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
+  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.mbitsT); cudaFree(sh.eamax); cudaFree(sh.i8_planes); cudaFree(sh.i8_aux); cudaFree(sh.i8_scratch); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
   cudaFree(sh.partials); cudaFree(sh.scratch);
   if (sh.tmap) free(sh.tmap);
   if (sh.ev0) cudaEventDestroy(sh.ev0);
