@@ -13,6 +13,12 @@ static int run_ppca(bool missing, const double* Y, int64_t D, int64_t N, int64_t
   if (!Y || !W0) return fail(GPLVM_ERR_ARG, "gplvm_ppca: null input");
   if (stop_kind != GPLVM_STOP_ITERATIONS && stop_kind != GPLVM_STOP_TOLERANCE)
     return fail(GPLVM_ERR_ARG, "gplvm_ppca: unknown stop_kind %d", stop_kind);
+  // One-shot calls own the whole matrix.  After gplvm_dist_init(world > 1) every rank would build a session over all N
+  // observations and the per-step all-reduce would add `world` copies of the statistics: refuse (use the session API
+  // with this rank's block, or gplvm_set_devices in a single process).
+  if (ctx().multiproc && ctx().world > 1)
+    return fail(GPLVM_ERR_STATE, "gplvm_ppca*: one-shot calls are single-process (gplvm_set_devices); this process is rank %d of %d "
+                "(gplvm_dist_init) -- use the session API with this rank's observation block", ctx().rank, ctx().world);
   gplvm_ppca_session* s = nullptr;
   GP_TRY(gplvm_session_create(D, N, M, missing ? 1 : 0, 0, N, &s));
   int rc = gplvm_session_load_host(s, Y, N);

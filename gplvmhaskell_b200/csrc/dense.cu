@@ -578,11 +578,6 @@ int dense_init_constants(gplvm_ppca_session* s) {
     }
     GP_TRY(dense_centre(s, -1.0));
     s->centred = true;
-    if (dense_i8_enabled() && s->use_dmma)
-      for (ShardState& sh : s->sh) {
-        CUDA_TRY(cudaSetDevice(sh.dev));
-        GP_TRY(dense_i8_prepare(s, sh));
-      }
     GP_TRY(launch_moments(s, 3));
     GP_TRY(session_allreduce_stats(s, s->D));
     for (ShardState& sh : s->sh) {
@@ -600,11 +595,11 @@ int dense_init_constants(gplvm_ppca_session* s) {
 
 // statistics pass with projection matrix proj (D x MP): fills sh.stats (local sums)
 static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double* proj, bool em_step = false) {
-  if (em_step && sh.i8_planes) return dense_i8_stats(s, sh, proj);   // experimental, GPLVM_DENSE_I8=1 only
   if (s->use_dmma) return dense_dmma_stats(s, sh, proj);
   const int MP = s->MP, D = (int)s->D;
   const size_t smem = sizeof(double) * (64 * MP + 32 * 65);
   GP_LAUNCH(dense_ez_kernel, (unsigned)ceil_div(sh.n, 32), 256, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, proj, sh.Ez);
+  seg_mark(sh, 1);   // generic path: segment 0 = E[z] kernel, segment 1 = statistics GEMM + reduction
   const int R = D + MP;
   return launch_stats_gemm(sh, ROWS_DENSE, D, R, R, MP, MP, sh.Ez, MP, MP, nullptr, 0, s->S, sh.stats);
 }
@@ -615,6 +610,7 @@ int dense_enqueue_step(gplvm_ppca_session* s) {
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (sh.evk0) CUDA_TRY(cudaEventRecord(sh.evk0, sh.st));
+    seg_mark(sh, 0);
     if (p2p_step) {
       sh.peer_args.peers = sh.peers_dev;
       sh.peer_args.world = ctx().world;
@@ -638,11 +634,13 @@ int dense_enqueue_step(gplvm_ppca_session* s) {
       CUDA_TRY(cudaFuncSetAttribute(dense_update16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
       attr_done[sh.dev & 63] = true;
     }
+    seg_mark(sh, 2);
     if (fast16) {
       GP_LAUNCH(dense_update16_kernel, 1, 256, smem16, sh.st, sh.par, sh.stats);
     } else {
       GP_LAUNCH(dense_update_kernel, 1, 256, smem, sh.st, sh.par, sh.stats);
     }
+    seg_mark(sh, 3);
   }
   return GPLVM_OK;
 }

@@ -370,6 +370,7 @@ int dense_dmma_prepare(gplvm_ppca_session* s) {
 int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj) {
   int grid = 0;
   GP_TRY(dispatch_dmma<MODE_DENSE>(s, sh, proj, s->S, MaskedArgs(), &grid));
+  seg_mark(sh, 1);
   return launch_reduce_partials(sh, s->S, grid);
 }
 

@@ -566,7 +566,7 @@ int masked_init_constants(gplvm_ppca_session* s) {
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     GP_LAUNCH(masked_bits_kernel, (unsigned)ceil_div(sh.n, 8), 256, 0, sh.st, sh.X, sh.ldx, sh.n, (int)s->D, s->WPR, sh.mbits);
-    if (sh.mbitsT) GP_TRY(masked_use_legacy_imma() ? masked_imma_prepare(s, sh) : masked_utc_prepare(s, sh));
+    if (sh.mbitsT) GP_TRY(masked_utc_prepare(s, sh));
   }
   GP_TRY(moments_pass(s, 2));
   GP_TRY(session_allreduce_stats(s, 3 * s->D));
@@ -622,14 +622,19 @@ int masked_enqueue_step(gplvm_ppca_session* s) {
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (sh.evk0) CUDA_TRY(cudaEventRecord(sh.evk0, sh.st));
+    seg_mark(sh, 0);
     double* s2dst = sh.stats + (int64_t)(D + 1) * s->EAS;
     if (s->use_dmma) {
       // fused path (M = 16): b_i by TMA + DMMA, per-observation register solver, sparse complement sums, S2 by DMMA
       GP_TRY(masked_dmma_b(s, sh, sh.par.W, sh.par.mu, sh.Ez, sh.yy));
+      seg_mark(sh, 1);
       GP_TRY(masked_fused_solve(s, sh, sh.Ez, sh.yy, false, nullptr));
+      seg_mark(sh, 2);
       if (D >= 128) GP_TRY(masked_fused_miss_sums(s, sh, sh.stats));
       else GP_TRY(launch_miss_sums(s, sh));
+      seg_mark(sh, 3);
       GP_TRY(masked_dmma_s2(s, sh, sh.EA + s->NV, s->EAS, s2dst));
+      seg_mark(sh, 4);
     } else {
       const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(sh.n, EW), 148 * 8);
       GP_LAUNCH(masked_estep_kernel, grid, EW * 32, smem, sh.st, sh.X, sh.ldx, sh.n, sh.par, sh.EA, s->EAS);
@@ -642,8 +647,10 @@ int masked_enqueue_step(gplvm_ppca_session* s) {
   GP_TRY(session_allreduce_stats(s, s->S));
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
+    if (s->use_dmma) seg_mark(sh, 5);
     GP_LAUNCH(masked_update_kernel, (unsigned)ceil_div(D, EW), EW * 32, smem, sh.st, sh.par, sh.stats, sh.scratch);
     GP_LAUNCH(masked_finalize_kernel, 1, 256, 0, sh.st, sh.par, sh.stats, sh.scratch);
+    if (s->use_dmma) seg_mark(sh, 6);
   }
   return GPLVM_OK;
 }

@@ -15,6 +15,7 @@
 //              by __shfl_sync; reciprocals by rcp.approx.f64 + 2 Newton steps; log det M_i = sum log pivots.
 //   outputs  : ez = M_i^-1 b, A_i = ez ez^T + sigma^2 M_i^-1.
 // b_i (and |y_c|^2 for the likelihood) come from the TMA + DMMA pass in dense_dmma.cu (MODE_MASKED_B).
+#include "masked_fx.cuh"
 #include "ppca.cuh"
 #include "tma.cuh"
 
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_ker
   const int64_t stride = (int64_t)gridDim.x * (SOLVE_WARPS * SOLVE_ROWS);
   const int64_t iters = (n_obs > cta0) ? (n_obs - cta0 + stride - 1) / stride : 0;
   double llacc = 0.0;
-  uint32_t mxa = 0u, mxe = 0u;   // high words of the largest |vech A| and |ez| entries written (scale of masked_imma.cu)
+  uint32_t mxa = 0u, mxe = 0u;   // high words of the largest |vech A| and |ez| entries written (fixed-point scale, masked_fx.cuh)
   const double log2pi = 1.8378770664093453, logs2 = LL ? log(s2) : 0.0;
 
   for (int64_t it = 0; it < iters; ++it) {
@@ -432,17 +433,16 @@ int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc
 
 // complement sums [G^miss | S1^miss] (D x 152) + totals (152) into dst (length (D + 1) x 152)
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
-  // default: exact fixed-point sums on the INT8 tensor cores (tcgen05: masked_utc.cu; legacy mma.sync with
-  // GPLVM_MISS_IMMA=1: masked_imma.cu), followed by the FP64 DMMA product as a
-  // device-side fallback that runs only when the precision guard of the INT8 path fired (its `scal` block is the guard's:
+  // default: exact fixed-point sums on the INT8 tensor cores (tcgen05, masked_utc.cu), followed by the FP64 DMMA
+  // product as a device-side fallback that runs only when the precision guard of the INT8 path fired (its `scal` block is the guard's:
   // S_DONE = 1.0 makes both kernels return at once).  GPLVM_MISS_DMMA=1 selects the FP64 product unconditionally.
   static const bool force_dmma = []() {
     const char* e = getenv("GPLVM_MISS_DMMA");
     return e ? (atoi(e) != 0) : false;
   }();
   const bool imma = !force_dmma && sh.mbitsT;
-  if (imma) GP_TRY(masked_use_legacy_imma() ? masked_imma_miss_sums(s, sh, dst) : masked_utc_miss_sums(s, sh, dst));
-  double* scal = imma ? masked_imma_guard_scal(sh) : sh.par.scal;
+  if (imma) GP_TRY(masked_utc_miss_sums(s, sh, dst));
+  double* scal = imma ? fx::guard_scal(sh.eamax) : sh.par.scal;
   const int64_t Spart = (int64_t)(s->D + 1) * EASF;
   const int fgroups = (int)std::max<int64_t>(1, s->D / 128);
   int rb = (int)std::min<int64_t>(std::max<int64_t>(1, sm_count(sh.dev) / fgroups), sh.nparts);
@@ -456,14 +456,6 @@ int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst) {
   }
   GP_TRY(rc);
   return launch_reduce_partials(sh, Spart, rb, dst, scal);
-}
-
-bool masked_use_legacy_imma() {
-  static const bool legacy = []() {
-    const char* e = getenv("GPLVM_MISS_IMMA");
-    return e ? (atoi(e) != 0) : false;
-  }();
-  return legacy;
 }
 
 }  // namespace gplvm

@@ -1,5 +1,20 @@
-// masked_fx.cuh -- fixed-point conventions shared by the INT8 complement-sum kernels (masked_imma.cu: legacy
-// mma.sync path, masked_utc.cu: tcgen05 path).  See masked_imma.cu for the derivation.
+// masked_fx.cuh -- fixed-point conventions of the INT8 complement-sum kernel (masked_utc.cu, tcgen05 kind::i8).
+//
+//   miss (D x 152) = Miss^T (D x n) . [vech A | ez] (n x 152),   Miss[i][d] = 1 when observation i misses feature d
+// (reference: the per-feature sums over the observations that miss / have the feature, emStepsMissed.stepTwo,
+// src/GPLVM/PPCA.hs:119-147; complement form).
+//
+// One factor is exactly 0 / 1, so only the other needs splitting: every [vech A | ez] entry v is rounded ONCE to the
+// fixed-point grid of its column class,  x = rint(v 2^(51 - E)),  |v| < 2^E  (E from the largest |entry| of the class --
+// vech A or ez -- which the solver kernel tracks with an integer max), and  u = x + 2^51  in [0, 2^52] is cut into its
+// 7 bytes.  Byte planes are u8 B-operands, the mask bits expand to s8 A-operands, the products accumulate exactly in
+// s32, and a constant-1 column counts the offsets:  sum_i x_i = sum_s 256^s S_s - 2^51 cnt.  All sums are integers =>
+// independent of the summation order and of the split of the observations over CTAs: bitwise reproducible.  The one
+// rounding per entry is <= 2^-52 of the class maximum, i.e. no worse than the rounding of a single FP64 addition of that
+// entry into a running sum; the accumulated sum itself is exact and is rounded to FP64 once at the end.
+// Precision guard: the cutting threads count (sampled) the entries more than 2^20 below their class maximum; above 1 %
+// the finalize kernel hands the step to the FP64 product of masked_fused.cu on the device.
+// oracle/fixedpoint.py restates the arithmetic on the CPU (tests only).
 #pragma once
 #include "ppca.cuh"
 

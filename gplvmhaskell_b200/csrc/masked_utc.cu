@@ -1,6 +1,6 @@
-// masked_utc.cu -- the exact fixed-point complement sums of masked_imma.cu on the 5th-generation tensor cores:
+// masked_utc.cu -- exact fixed-point complement sums of the masked M-step on the 5th-generation tensor cores:
 // tcgen05.mma kind::i8 (s8 x u8 -> s32 accumulators in TMEM; 4.41 POP/s measured on B200, tools/tcgen05_i8_peak.cu,
-// 3.9x the legacy mma.sync path).  Same arithmetic, bit-identical results: see masked_imma.cu / masked_fx.cuh.
+// 3.9x the legacy mma.sync IMMA path).  Arithmetic and derivation: masked_fx.cuh.
 //
 //   D[f][n] (TMEM, 128 lanes x 144 columns per 128 features)  +=  A[f][k] . B[n][k]      k = observation
 //   A = mask bytes (0 / 1),  B row 7 c + s = byte plane s of column c of [vech A | ez],  B row 133 = 1 (offset count)

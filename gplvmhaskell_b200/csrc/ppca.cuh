@@ -65,10 +65,7 @@ struct ShardState {
   uint32_t* mbits = nullptr;   // masked: n x WPR words, bit d set = feature d of the observation is missing
   uint32_t* mbitsT = nullptr;  // masked fused path: D x nwT words, bit j of word w = observation 32 w + j misses the feature
   int64_t nwT = 0;             //   4 x ceil(n / 128) words per feature
-  uint8_t* i8_planes = nullptr;   // experimental INT8 dense statistics (dense_i8.cu, GPLVM_DENSE_I8=1): byte planes of Xc,
-  uint8_t* i8_aux = nullptr;      //   feature maxima / scales / projector planes,
-  long long* i8_scratch = nullptr;  //   per-CTA int64 class sums
-  uint32_t* eamax = nullptr;   // masked fused path: 256 B block: class maxima of the last solve, precision-guard counters, guard flags (masked_imma.cu)
+  uint32_t* eamax = nullptr;   // masked fused path: 256 B block: class maxima of the last solve, precision-guard counters, guard flags (masked_fx.cuh)
   double* parblock = nullptr;  // parameter block
   double* stats = nullptr;     // packed statistics (all-reduced), `S` doubles
   double* partials = nullptr;  // nparts x S
@@ -83,7 +80,19 @@ struct ShardState {
   int nparts = 0;
   Par par;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  // per-kernel timing of one EM step (gplvm_session_set_kernel_timing): mark i is recorded before segment i starts
+  static constexpr int MAX_MARKS = 10;
+  cudaEvent_t evseg[MAX_MARKS] = {};
+  int nmarks = 0;   // marks recorded by the last step
 };
+
+// record segment mark `i` on the shard's stream when per-kernel timing is on (no-op otherwise)
+inline void seg_mark(ShardState& sh, int i) {
+  if (sh.evk0 && i < ShardState::MAX_MARKS && sh.evseg[i]) {
+    cudaEventRecord(sh.evseg[i], sh.st);
+    if (i + 1 > sh.nmarks) sh.nmarks = i + 1;
+  }
+}
 
 }  // namespace gplvm
 
@@ -113,18 +122,11 @@ bool dense_dmma_eligible(const gplvm_ppca_session* s);
 int dense_dmma_prepare(gplvm_ppca_session* s);
 int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int dense_dmma_release(gplvm_ppca_session* s);
-bool dense_i8_enabled();
-int dense_i8_prepare(gplvm_ppca_session* s, ShardState& sh);
-int dense_i8_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj);
 int masked_dmma_b(gplvm_ppca_session* s, ShardState& sh, const double* W, const double* mu, double* bout, double* yyout);
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out);
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
-int masked_imma_prepare(gplvm_ppca_session* s, ShardState& sh);
-int masked_imma_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
-double* masked_imma_guard_scal(ShardState& sh);
 int masked_utc_prepare(gplvm_ppca_session* s, ShardState& sh);
 int masked_utc_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
-bool masked_use_legacy_imma();   // GPLVM_MISS_IMMA=1: mma.sync IMMA kernel instead of the tcgen05 one
 int masked_dmma_s2(gplvm_ppca_session* s, ShardState& sh, const double* ez, int64_t ldez, double* dst);
 int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
 // masked.cu

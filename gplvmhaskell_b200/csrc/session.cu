@@ -10,12 +10,13 @@ int dense_centre(gplvm_ppca_session* s, double sign);
 
 namespace {
 
-// out (cols x ld_out) <- in^T, in is (rows x ld_in); 32x32 tiles through shared memory
+// out (cols x ld_out) <- in^T, in is (rows x ld_in); 32x32 tiles through shared memory.  rows_on_x: the row tiles of `in`
+// ride on gridDim.x (the observation axis always does: gridDim.y is limited to 65535 tiles)
 __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int64_t ld_in, double* __restrict__ out,
-                                                        int64_t ld_out, int64_t rows, int64_t cols) {
+                                                        int64_t ld_out, int64_t rows, int64_t cols, int rows_on_x) {
   __shared__ double t[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  const int64_t c0 = (int64_t)(rows_on_x ? blockIdx.y : blockIdx.x) * 32, r0 = (int64_t)(rows_on_x ? blockIdx.x : blockIdx.y) * 32;
   for (int j = ty; j < 32; j += 8) {
     const int64_t r = r0 + j, c = c0 + tx;
     t[j][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.0;
@@ -86,13 +87,15 @@ int64_t chunk_obs(int64_t D) {
 
 void free_shard(ShardState& sh) {
   cudaSetDevice(sh.dev);
-  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.mbitsT); cudaFree(sh.eamax); cudaFree(sh.i8_planes); cudaFree(sh.i8_aux); cudaFree(sh.i8_scratch); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
+  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.mbitsT); cudaFree(sh.eamax); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
   cudaFree(sh.partials); cudaFree(sh.scratch);
   if (sh.tmap) free(sh.tmap);
   if (sh.ev0) cudaEventDestroy(sh.ev0);
   if (sh.ev1) cudaEventDestroy(sh.ev1);
   if (sh.evk0) cudaEventDestroy(sh.evk0);
   if (sh.evk1) cudaEventDestroy(sh.evk1);
+  for (cudaEvent_t e : sh.evseg)
+    if (e) cudaEventDestroy(e);
   sh = ShardState();
 }
 
@@ -206,21 +209,33 @@ void session_release_p2p(gplvm_ppca_session* s) {
   s->p2p = false;
 }
 
-static int check_async(gplvm_ppca_session* s, double* scal_out) {
-  // synchronise every shard and surface numeric failures
-  double scal[S_COUNT];
+// Synchronise every shard and surface numeric failures.  collective: in multi-process mode the ranks exchange their
+// error flags (S_ERR is rank-local: an all-NaN observation or a non positive definite M_i lives in one shard), so that every
+// rank leaves a collective entry point (init / steps+sync / run) with the same verdict instead of one rank returning an
+// error while its peers wait in the next all-reduce or return statistics poisoned by the failed shard.
+static int check_async(gplvm_ppca_session* s, double* scal_out, bool collective = false) {
+  double scal[S_COUNT], first[S_COUNT];
+  double worst = 0.0;
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     CUDA_TRY(cudaMemcpyAsync(scal, sh.par.scal, sizeof scal, cudaMemcpyDeviceToHost, sh.st));
     CUDA_TRY(cudaStreamSynchronize(sh.st));
-    if (scal[S_ERR] == 2.0)
-      return fail(GPLVM_ERR_UNSUPPORTED, "missing-data PPCA: an observation has every feature missing (unsupported by the reference, Util.hs:81)");
-    if (scal[S_ERR] == 3.0)
-      return fail(GPLVM_ERR_NCCL, "a bounded device-side wait expired (peer statistics exchange: a rank did not publish its statistics; or the tcgen05 producer / MMA handshake of the masked complement sums)");
-    if (scal[S_ERR] != 0.0)
-      return fail(GPLVM_ERR_NUMERIC, "PPCA: a matrix that must be positive definite is not (step %lld)", (long long)scal[S_STEPS]);
-    if (&sh == &s->sh[0] && scal_out) memcpy(scal_out, scal, sizeof scal);
+    if (scal[S_ERR] > worst) worst = scal[S_ERR];   // 3 (expired wait) > 2 (all-NaN observation) > 1 (not positive definite)
+    if (&sh == &s->sh[0]) memcpy(first, scal, sizeof scal);
   }
+  if (collective && ctx().multiproc && ctx().world > 1) {
+    std::vector<double> all(ctx().world, 0.0);
+    GP_TRY(allgather_bytes(&worst, all.data(), sizeof(double)));
+    for (double v : all)
+      if (v > worst) worst = v;
+  }
+  if (worst == 2.0)
+    return fail(GPLVM_ERR_UNSUPPORTED, "missing-data PPCA: an observation has every feature missing (unsupported by the reference, Util.hs:81)");
+  if (worst == 3.0)
+    return fail(GPLVM_ERR_NCCL, "a bounded device-side wait expired (peer statistics exchange: a rank did not publish its statistics; or the tcgen05 producer / MMA handshake of the masked complement sums)");
+  if (worst != 0.0)
+    return fail(GPLVM_ERR_NUMERIC, "PPCA: a matrix that must be positive definite is not (step %lld)", (long long)first[S_STEPS]);
+  if (scal_out) memcpy(scal_out, first, sizeof first);
   return GPLVM_OK;
 }
 
@@ -245,6 +260,24 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
   std::lock_guard<std::recursive_mutex> lk(c.mu);
   if (!c.multiproc && (obs_begin != 0 || obs_count != N_global))
     return fail(GPLVM_ERR_ARG, "session_create: partial observation blocks need gplvm_dist_init (multi-process mode)");
+  if (c.multiproc && c.world > 1) {
+    // the rank blocks must partition [0, N) in rank order and describe the same problem: overlapping blocks would be
+    // summed `world` times by the all-reduce while N stays N (silently wrong W and sigma2)
+    struct Desc { int64_t D, N, M, missing, begin, count; } mine{D, N_global, M, missing != 0, obs_begin, obs_count};
+    std::vector<Desc> all(c.world);
+    GP_TRY(allgather_bytes(&mine, all.data(), sizeof(Desc)));
+    int64_t next = 0;
+    for (int r = 0; r < c.world; ++r) {
+      if (all[r].D != D || all[r].N != N_global || all[r].M != M || all[r].missing != (missing != 0))
+        return fail(GPLVM_ERR_ARG, "session_create: rank %d describes a different problem (D, N, M, missing)", r);
+      if (all[r].begin != next)
+        return fail(GPLVM_ERR_ARG, "session_create: the rank blocks do not partition [0, %lld): rank %d starts at %lld, expected %lld",
+                    (long long)N_global, r, (long long)all[r].begin, (long long)next);
+      next += all[r].count;
+    }
+    if (next != N_global)
+      return fail(GPLVM_ERR_ARG, "session_create: the rank blocks cover %lld of %lld observations", (long long)next, (long long)N_global);
+  }
   auto* s = new gplvm_ppca_session();
   s->D = D; s->N = N_global; s->M = M; s->missing = missing != 0;
   s->use_dmma = dense_dmma_eligible(s);
@@ -260,14 +293,15 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
   const int nsh = (int)c.shards.size();
   int used = nsh;
   if (obs_count < used) used = (int)obs_count;
-  const int64_t per = ceil_div(obs_count, used);
+  // balanced split: the first obs_count % used shards take one observation more, so no shard is ever empty
+  const int64_t base = obs_count / used, extra = obs_count % used;
   s->sh.resize(used);
   for (int i = 0; i < used; ++i) {
     ShardState& sh = s->sh[i];
     sh.dev = c.shards[i].device;
     sh.st = c.shards[i].stream;
-    sh.n0 = obs_begin + per * i;
-    sh.n = std::min<int64_t>(per, obs_begin + obs_count - sh.n0);
+    sh.n0 = obs_begin + base * i + std::min<int64_t>(i, extra);
+    sh.n = base + (i < extra ? 1 : 0);
   }
   if (used != nsh) {
     delete s;
@@ -284,7 +318,7 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
     if (e == cudaSuccess) e = cudaMalloc(&sh.X, sizeof(double) * (size_t)sh.n * sh.ldx);
     if (e == cudaSuccess && (s->missing == s->use_dmma)) e = cudaMalloc(&sh.Ez, sizeof(double) * (size_t)sh.n * MP);  // generic dense Ez / fused masked b
     if (e == cudaSuccess && s->missing && s->use_dmma) e = cudaMalloc(&sh.yy, sizeof(double) * (size_t)sh.n);
-    if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.EA, sizeof(double) * ((size_t)round_up(sh.n, 128) * s->EAS + 8));  // whole 128-observation chunks (masked_imma.cu)
+    if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.EA, sizeof(double) * ((size_t)round_up(sh.n, 128) * s->EAS + 8));  // whole 128-observation chunks (masked_utc.cu)
     if (e == cudaSuccess && s->missing) e = cudaMalloc(&sh.mbits, sizeof(uint32_t) * (size_t)(sh.n + 64) * s->WPR + 64);  // padded: whole-tile bulk copies
     if (e == cudaSuccess && s->missing && s->use_dmma && (D == 128 || D == 256)) {
       sh.nwT = 4 * ceil_div(sh.n, (int64_t)128);
@@ -367,7 +401,7 @@ int gplvm_session_load_host(gplvm_ppca_session* s, const double* Y, int64_t ld) 
                                         cudaMemcpyHostToDevice, sh.st);
       if (e != cudaSuccess) { cudaFree(stage); return fail(GPLVM_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
       dim3 grid((unsigned)ceil_div(cn, 32), (unsigned)ceil_div(D, 32));
-      GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, stage, ch, sh.X + c0 * sh.ldx, sh.ldx, D, cn);
+      GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, stage, ch, sh.X + c0 * sh.ldx, sh.ldx, D, cn, 0);
     }
     CUDA_TRY(cudaStreamSynchronize(sh.st));
     CUDA_TRY(cudaFree(stage));
@@ -392,8 +426,8 @@ int gplvm_session_read_data(gplvm_ppca_session* s, double* Y, int64_t ld) {
     CUDA_TRY(cudaMalloc(&stage, sizeof(double) * (size_t)D * ch));
     for (int64_t c0 = 0; c0 < sh.n; c0 += ch) {
       const int64_t cn = std::min(ch, sh.n - c0);
-      dim3 grid((unsigned)ceil_div(D, 32), (unsigned)ceil_div(cn, 32));
-      GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, sh.X + c0 * sh.ldx, sh.ldx, stage, ch, cn, D);
+      dim3 grid((unsigned)ceil_div(cn, 32), (unsigned)ceil_div(D, 32));
+      GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, sh.X + c0 * sh.ldx, sh.ldx, stage, ch, cn, D, 1);
       double* dst = Y + (sh.n0 - first) + c0;
       cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * ld, stage, sizeof(double) * ch, sizeof(double) * cn, D,
                                         cudaMemcpyDeviceToHost, sh.st);
@@ -437,7 +471,7 @@ int gplvm_session_init(gplvm_ppca_session* s, const double* W0, double sigma2_0)
   }
   s->steps = 0;
   GP_TRY(s->missing ? masked_init_constants(s) : dense_init_constants(s));
-  GP_TRY(check_async(s, nullptr));
+  GP_TRY(check_async(s, nullptr, true));
   s->initialised = true;
   return GPLVM_OK;
 }
@@ -462,7 +496,7 @@ int gplvm_session_steps(gplvm_ppca_session* s, int64_t steps) {
 int gplvm_session_sync(gplvm_ppca_session* s) {
   if (!s) return fail(GPLVM_ERR_ARG, "session_sync: null session");
   std::lock_guard<std::recursive_mutex> lk(ctx().mu);
-  return check_async(s, nullptr);
+  return check_async(s, nullptr, true);
 }
 
 int gplvm_session_run(gplvm_ppca_session* s, int stop_kind, int64_t k, double tol, int64_t* steps_done) {
@@ -474,7 +508,7 @@ int gplvm_session_run(gplvm_ppca_session* s, int stop_kind, int64_t k, double to
     // Left k: continue while k > iteration, iteration starting at 0  =>  max(k,0)+1 steps (PPCA.hs:91)
     const int64_t total = (k > 0 ? k : 0) + 1;
     GP_TRY(gplvm_session_steps(s, total));
-    GP_TRY(check_async(s, scal));
+    GP_TRY(check_async(s, scal, true));
   } else if (stop_kind == GPLVM_STOP_TOLERANCE) {
     // Right tol: the update kernel raises DONE once max(|ds2|, max|dW|) <= tol; later steps are no-ops.
     for (ShardState& sh : s->sh) {
@@ -486,7 +520,7 @@ int gplvm_session_run(gplvm_ppca_session* s, int stop_kind, int64_t k, double to
     for (int64_t done = 0; done < cap;) {
       GP_TRY(gplvm_session_steps(s, batch));
       done += batch;
-      GP_TRY(check_async(s, scal));
+      GP_TRY(check_async(s, scal, true));
       if (scal[S_DONE] != 0.0) break;
       if (batch < 64) batch *= 2;
     }
@@ -494,7 +528,7 @@ int gplvm_session_run(gplvm_ppca_session* s, int stop_kind, int64_t k, double to
       CUDA_TRY(cudaSetDevice(sh.dev));
       GP_LAUNCH(set_scal_kernel, 1, 1, 0, sh.st, sh.par.scal, (int)S_USETOL, 0.0, (int)S_DONE, 0.0);
     }
-    GP_TRY(check_async(s, nullptr));
+    GP_TRY(check_async(s, nullptr, true));
   } else {
     return fail(GPLVM_ERR_ARG, "session_run: unknown stop_kind %d", stop_kind);
   }
@@ -555,9 +589,16 @@ int gplvm_session_set_kernel_timing(gplvm_ppca_session* s, int on) {
     if (on && !sh.evk0) {
       CUDA_TRY(cudaEventCreate(&sh.evk0));
       CUDA_TRY(cudaEventCreate(&sh.evk1));
+      for (cudaEvent_t& e : sh.evseg) CUDA_TRY(cudaEventCreate(&e));
+      sh.nmarks = 0;
     } else if (!on && sh.evk0) {
       cudaEventDestroy(sh.evk0); cudaEventDestroy(sh.evk1);
       sh.evk0 = sh.evk1 = nullptr;
+      for (cudaEvent_t& e : sh.evseg) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+      }
+      sh.nmarks = 0;
     }
   }
   return GPLVM_OK;
@@ -582,6 +623,37 @@ int gplvm_session_last_steps_ms(gplvm_ppca_session* s, double* total_ms, double*
   if (total_ms) *total_ms = tmax;
   if (kernel_ms) *kernel_ms = kmax;
   return GPLVM_OK;
+}
+
+// Per-kernel device times of the LAST EM step enqueued while kernel timing was on (max over the local GPUs).
+static const char* const kDenseSegments[] = {"statistics kernel (X.A, X^T.Ez, Ez^T.Ez)", "partial reduction + all-reduce", "replicated update"};
+static const char* const kMaskedSegments[] = {"b pass (TMA + DMMA)", "per-observation solver", "complement sums (tcgen05 INT8)",
+                                              "S2 pass (TMA + DMMA)", "all-reduce", "replicated update + finalize"};
+
+int gplvm_session_last_segments_ms(gplvm_ppca_session* s, double* ms_out, int capacity, int* n_out) {
+  if (!s || !n_out) return fail(GPLVM_ERR_ARG, "null argument");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  *n_out = 0;
+  int nseg = 0;
+  for (ShardState& sh : s->sh) {
+    if (!sh.evk0 || sh.nmarks < 2) continue;
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    CUDA_TRY(cudaEventSynchronize(sh.evseg[sh.nmarks - 1]));
+    nseg = sh.nmarks - 1;
+    for (int i = 0; i < nseg && i < capacity; ++i) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, sh.evseg[i], sh.evseg[i + 1]));
+      if (&sh == &s->sh[0] || ms > ms_out[i]) ms_out[i] = ms;
+    }
+  }
+  *n_out = nseg < capacity ? nseg : capacity;
+  return GPLVM_OK;
+}
+
+const char* gplvm_session_segment_name(gplvm_ppca_session* s, int i) {
+  if (!s || i < 0) return "";
+  if (s->missing) return i < 6 ? kMaskedSegments[i] : "";
+  return i < 3 ? kDenseSegments[i] : "";
 }
 
 }  // extern "C"

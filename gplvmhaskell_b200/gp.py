@@ -47,6 +47,10 @@ def gp_chol_lml(X, y, inv_lengthscale2, variance: float = 1.0, jitter: float = 0
     N, Q = X.shape
     il2 = np.ascontiguousarray(np.asarray(inv_lengthscale2, dtype=np.float64).reshape(-1))
     yv = None if y is None else np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    if il2.shape[0] != Q:
+        raise ValueError("inv_lengthscale2 must have Q = %d entries" % Q)
+    if yv is not None and yv.shape[0] != N:
+        raise ValueError("y must have N = %d entries" % N)
     L = np.empty((N, N), dtype=np.float64) if want_factor else None
     lml, logdet = C.c_double(), C.c_double()
     _lib.check(lib.gplvm_gp_chol_lml(_lib.dptr(X), N, Q, _lib.dptr(yv), _lib.dptr(il2), float(variance), float(jitter),
@@ -58,6 +62,8 @@ def cholesky(A) -> np.ndarray:
     """Lower Cholesky factor (cholSH with the factor taken as lower)."""
     lib = _lib.load()
     A = np.ascontiguousarray(A, dtype=np.float64)
+    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+        raise ValueError("A must be square")
     N = A.shape[0]
     L = np.empty((N, N), dtype=np.float64)
     _lib.check(lib.gplvm_cholesky(_lib.dptr(A), N, _lib.dptr(L)))
@@ -68,6 +74,10 @@ def tri_solve_lower(L, B) -> np.ndarray:
     """Solve L X = B for lower-triangular L (linearSolveS cholK ..., GaussianProcess.hs:74,77)."""
     lib = _lib.load()
     L = np.ascontiguousarray(L, dtype=np.float64)
+    if L.ndim != 2 or L.shape[0] != L.shape[1]:
+        raise ValueError("L must be square")
+    if np.asarray(B).shape[0] != L.shape[0]:
+        raise ValueError("B must have N = %d rows" % L.shape[0])
     B2 = np.ascontiguousarray(np.asarray(B, dtype=np.float64).reshape(L.shape[0], -1))
     X = np.empty_like(B2)
     _lib.check(lib.gplvm_tri_solve_lower(_lib.dptr(L), L.shape[0], _lib.dptr(B2), B2.shape[1], _lib.dptr(X)))
@@ -85,6 +95,10 @@ def gp_to_posterior_sample(observe, x_train, y_train, normals=None, inv_lengthsc
     yt = np.ascontiguousarray(np.asarray(y_train, dtype=np.float64).reshape(-1))
     il2 = np.ascontiguousarray(np.asarray(inv_lengthscale2, dtype=np.float64).reshape(-1))
     no, nt, q = Xo.shape[0], Xt.shape[0], Xo.shape[1]
+    if Xt.shape[1] != q or il2.shape[0] != q:
+        raise ValueError("observe, x_train and inv_lengthscale2 must agree on the input dimension Q")
+    if yt.shape[0] != nt:
+        raise ValueError("y_train must have n_train = %d entries" % nt)
     mean = np.empty(no)
     post = np.empty((no, no))
     samples = None

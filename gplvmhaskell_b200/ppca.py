@@ -79,8 +79,13 @@ def _draw_init(gen, d: int, m: int):
 def _run(Y: np.ndarray, M: int, stop, W0: np.ndarray, s20: float, which: str):
     lib = _lib.load()
     Y = np.ascontiguousarray(Y, dtype=np.float64)
+    if Y.ndim != 2:
+        raise ValueError("learning vectors must be a D x N matrix")
     D, N = Y.shape
     W0 = np.ascontiguousarray(W0, dtype=np.float64)
+    # the C ABI copies D * M doubles from W0: a smaller buffer would be read out of bounds
+    if W0.shape != (D, int(M)):
+        raise ValueError("W0 must be D x M = %d x %d, got %s" % (D, int(M), "x".join(map(str, W0.shape))))
     kind, val = stop
     stop_kind = _lib.STOP_ITERATIONS if kind == "left" else _lib.STOP_TOLERANCE
     k = int(val) if kind == "left" else 0
@@ -113,13 +118,19 @@ def _run(Y: np.ndarray, M: int, stop, W0: np.ndarray, s20: float, which: str):
 
 def em_steps_fast(Y, W0, sigma2_0, stop: Stop):
     """emStepsFast (PPCA.hs:54-94): returns (W, variance, expLogLikelihood, None)."""
-    _, W, s2, ll, _, steps = _run(Y, np.asarray(W0).shape[1], _normalise_stop(stop), W0, sigma2_0, "dense")
+    W0 = np.asarray(W0, dtype=np.float64)
+    if W0.ndim != 2:
+        raise ValueError("W0 must be a D x M matrix")
+    _, W, s2, ll, _, steps = _run(Y, W0.shape[1], _normalise_stop(stop), W0, sigma2_0, "dense")
     return W, s2, ll, None
 
 
 def em_steps_missed(Y, W0, sigma2_0, stop: Stop):
     """emStepsMissed (PPCA.hs:96-182): returns (W, variance, expLogLikelihood, restored)."""
-    _, W, s2, ll, restored, steps = _run(Y, np.asarray(W0).shape[1], _normalise_stop(stop), W0, sigma2_0, "missing")
+    W0 = np.asarray(W0, dtype=np.float64)
+    if W0.ndim != 2:
+        raise ValueError("W0 must be a D x M matrix")
+    _, W, s2, ll, restored, steps = _run(Y, W0.shape[1], _normalise_stop(stop), W0, sigma2_0, "missing")
     return W, s2, ll, restored
 
 
@@ -214,9 +225,15 @@ class Session:
     def load_host(self, Y: np.ndarray, ld: Optional[int] = None):
         """Y: D x obs_count block (or a view into a D x ld matrix starting at this rank's first observation)."""
         Y = np.asarray(Y, dtype=np.float64)
+        if Y.ndim != 2 or Y.shape[0] != self.D:
+            raise ValueError("Y must have D = %d rows" % self.D)
         if ld is None:
             Y = np.ascontiguousarray(Y)
             ld = Y.shape[1]
+            if ld != self.obs_count:
+                raise ValueError("Y must be D x obs_count = %d x %d" % (self.D, self.obs_count))
+        elif ld < self.obs_count or Y.strides != (8 * ld, 8) or Y.shape[1] < self.obs_count:
+            raise ValueError("Y must be a row-major view with row stride ld >= obs_count covering this rank's block")
         _lib.check(self.lib.gplvm_session_load_host(self.h, _lib.dptr(Y), int(ld)))
 
     def synth(self, seed: int, nan_prob: float = 0.0):
@@ -268,6 +285,13 @@ class Session:
 
     def set_kernel_timing(self, on: bool):
         _lib.check(self.lib.gplvm_session_set_kernel_timing(self.h, int(on)))
+
+    def last_segments_ms(self):
+        """[(segment name, ms)] of the last EM step enqueued with kernel timing on."""
+        buf = (C.c_double * 16)()
+        n = C.c_int()
+        _lib.check(self.lib.gplvm_session_last_segments_ms(self.h, buf, 16, C.byref(n)))
+        return [(self.lib.gplvm_session_segment_name(self.h, i).decode(), buf[i]) for i in range(n.value)]
 
     def last_steps_ms(self):
         t, k = C.c_double(), C.c_double()

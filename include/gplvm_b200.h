@@ -130,8 +130,10 @@ int gplvm_dist_rank(void);
 int gplvm_dist_world(void);
 
 /* missing != 0 selects the NaN-masked path.  In multi-process mode obs_begin/obs_count describe this
- * rank's block of the global N; in single-process mode pass 0 / N (the library splits further over
- * gplvm_set_devices GPUs). */
+ * rank's block of the global N (collective: the blocks must partition [0, N) in rank order and agree on D, N, M,
+ * missing -- checked, GPLVM_ERR_ARG otherwise); in single-process mode pass 0 / N (the library splits further over
+ * gplvm_set_devices GPUs).  The one-shot calls above are single-process: after gplvm_dist_init(world > 1) they
+ * return GPLVM_ERR_STATE. */
 int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing,
                          int64_t obs_begin, int64_t obs_count, gplvm_ppca_session** out);
 int gplvm_session_destroy(gplvm_ppca_session* s);
@@ -158,7 +160,9 @@ int gplvm_session_steps(gplvm_ppca_session* s, int64_t steps);
 /* Run the reference stop rule from the current state; blocks. steps_done = EM steps executed so far. */
 int gplvm_session_run(gplvm_ppca_session* s, int stop_kind, int64_t k, double tol, int64_t* steps_done);
 
-/* Block until all enqueued work is done; returns the first asynchronous error. */
+/* Block until all enqueued work is done; returns the first asynchronous error.  In multi-process mode
+ * gplvm_session_init / _sync / _run are COLLECTIVE: the ranks exchange their error flags, so every rank returns the
+ * same status (a numeric failure or an all-NaN observation in one rank's block fails the call on all ranks). */
 int gplvm_session_sync(gplvm_ppca_session* s);
 
 /* Current parameters (host buffers, any may be NULL): W (D x M), sigma2, mu (D; feature means for the
@@ -180,6 +184,13 @@ int gplvm_session_set_kernel_timing(gplvm_ppca_session* s, int on);
  * local GPUs), measured with CUDA events on the launching streams; blocks until the batch is done.
  * kernel_ms (nullable) receives the summed duration of the dominant statistics kernel only. */
 int gplvm_session_last_steps_ms(gplvm_ppca_session* s, double* total_ms, double* kernel_ms);
+
+/* Per-kernel device times (ms) of the LAST EM step enqueued while kernel timing was on, max over the local GPUs:
+ * ms_out[i] = duration of segment i, *n_out segments written (<= capacity); gplvm_session_segment_name(s, i) names
+ * them (dense: statistics kernel | partial reduction + all-reduce | replicated update; masked: b pass | solver |
+ * complement sums | S2 pass | all-reduce | update).  Blocks until that step is done. */
+int gplvm_session_last_segments_ms(gplvm_ppca_session* s, double* ms_out, int capacity, int* n_out);
+const char* gplvm_session_segment_name(gplvm_ppca_session* s, int i);
 
 /* How this session combines the per-step statistics of the ranks: 0 = single GPU (nothing to combine), 1 = one packed
  * ncclAllReduce per step, 2 = all-reduce fused into the library's reduction kernel over NVLink peer memory (direct peer

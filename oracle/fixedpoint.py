@@ -1,7 +1,7 @@
 """oracle/fixedpoint.py -- TEST INFRASTRUCTURE (never imported by the product).
 
 CPU restatement (NumPy + Python integers) of the exact fixed-point arithmetic that the INT8 complement-sum kernels
-(gplvmhaskell_b200/csrc/masked_imma.cu, masked_utc.cu, masked_fx.cuh) use for
+(gplvmhaskell_b200/csrc/masked_utc.cu, masked_fx.cuh) use for
 
     miss (D x 152) = Miss^T (D x n) . [vech A | ez] (n x 152)          (reference: the per-feature sums of
                                                                         emStepsMissed.stepTwo, src/GPLVM/PPCA.hs:119-147)
@@ -88,7 +88,7 @@ def expand_order_word(std_word: int) -> int:
 
 
 def fragment_order_words(std_words: list[int]) -> list[int]:
-    """masked_imma.cu: word t, bit 8 b + 2 ks + h  <=>  observation 32 ks + 16 h + 4 t + b of the 128-observation chunk."""
+    """round-1 mma.sync IMMA kernel (removed in round 2, kept for the layout tests): word t, bit 8 b + 2 ks + h  <=>  observation 32 ks + 16 h + 4 t + b of the 128-observation chunk."""
     out = []
     for t in range(4):
         o = 0

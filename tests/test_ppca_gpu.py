@@ -212,7 +212,7 @@ def test_missing_steps_vs_oracle_synthetic(d, n, m, p):
 
 def test_missing_outlier_observation_takes_fp64_fallback():
     """One observation 2000x larger than the rest puts > 1 % of the [vech A | ez] entries more than 2^20 below the
-    class maximum: the precision guard of the INT8 complement sums (masked_imma.cu) must hand this step to the FP64
+    class maximum: the precision guard of the INT8 complement sums (masked_utc.cu / masked_fx.cuh) must hand this step to the FP64
     DMMA product on the device.  Tolerances are looser: tot - miss_d cancels ~7 digits with such an outlier."""
     Y, W0 = synth(256, 2048, 16, seed=99, nan_prob=0.2)
     Y[:, 5] *= 2000.0

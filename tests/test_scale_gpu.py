@@ -1,0 +1,161 @@
+"""GPU parity at benchmark scale: the CUDA path against the CPU oracle at sizes that reach the code only large inputs
+exercise -- TMA ring wrap-around (>= 4 tiles per CTA needs N >= 19k; 2^18 gives 55 tiles per CTA), multi-chunk TMEM
+accumulation of the INT8 complement sums (2^16 observations = 28 chunks per CTA), GP look-ahead over 64 panels --
+and the parameters the small tests never compared directly (mu', steps_done).
+
+The data is generated on the device by the bench generator (gplvm_session_synth), read back in
+the reference layout and handed to the oracle, so both sides see bit-identical inputs.
+
+Reference semantics held: src/GPLVM/PPCA.hs:63-82 (dense step), :106-147 (masked step), :149-168 (LL, restore),
+src/GPLVM/GaussianProcess.hs:67-68 (cholSH of K + jitter I).
+Tolerances: sigma2, LL 1e-9 relative, restored 1e-8 (BASELINE.json north_star); W, mu element-wise 1e-9 of max |.|.
+"""
+import numpy as np
+import pytest
+
+import gplvmhaskell_b200 as g
+from oracle import gp as ogp
+from oracle import ppca as oppca
+from conftest import rel
+
+pytestmark = pytest.mark.gpu
+
+D, M = 256, 16
+
+
+def test_dense_bench_scale_three_steps_vs_oracle():
+    """N = 2^18 (0.5 GB, beyond L2), D = 256, M = 16: 3 EM steps, each compared with oracle.dense_step."""
+    N = 1 << 18
+    W0 = np.random.default_rng(4321).standard_normal((D, M))
+    with g.Session(D, N, M, missing=False) as s:
+        s.synth(1234)
+        Y = s.read_data()
+        s.init(W0, 1.0)
+        Xc = oppca.center_dense(Y)
+        mean = oppca.mean_column(Y.T)
+        W, s2 = W0.copy(), 1.0
+        for step in range(1, 4):
+            s.steps(1)
+            p = s.params()
+            W, s2, mdw, dv = oppca.dense_step(Xc, W, s2)
+            assert p["steps"] == step
+            assert rel(p["W"], W) < 1e-10, (step, rel(p["W"], W))
+            assert abs(p["sigma2"] - s2) < 1e-10 * s2, (step, p["sigma2"], s2)
+            assert abs(p["max_dw"] - mdw) < 1e-9 * np.max(np.abs(W))
+            assert abs(p["dsigma2"] - dv) < 1e-9 * s2
+        assert rel(p["mu"], mean) < 1e-12
+        ll = s.loglik()
+    ll_ref = oppca.dense_loglik(Xc, W, s2, literal_det=False)
+    assert abs(ll - ll_ref) < 1e-9 * abs(ll_ref), (ll, ll_ref)
+
+
+def test_dense_run_left_k_matches_oracle_steps_done():
+    N = 50000   # ragged: not a multiple of the 16-row tile times the grid
+    W0 = np.random.default_rng(7).standard_normal((D, M))
+    with g.Session(D, N, M, missing=False) as s:
+        s.synth(99)
+        Y = s.read_data()
+    ref = oppca.em_steps_fast(Y, W0, 1.0, ("left", 2))
+    r = g.make_ppca(Y, M, g.Left(2), (W0, 1.0))
+    assert r.steps_done == ref.steps_done == 3
+    assert rel(r._W, ref.W) < 1e-10
+    assert abs(r._variance - ref.variance) < 1e-10 * ref.variance
+    assert abs(r._finalExpLikelihood - ref.final_exp_likelihood) < 1e-9 * abs(ref.final_exp_likelihood)
+
+
+def test_masked_bench_scale_two_steps_vs_oracle():
+    """N = 2^16, 20 % NaN: 2 EM steps vs missed_step_vectorised, comparing mu', W', sigma2' after EACH step, then LL and the
+    restored matrix (stale E-step, PPCA.hs:161-168) and steps_done on the Left k path."""
+    N = 1 << 16
+    W0 = np.random.default_rng(4321).standard_normal((D, M))
+    with g.Session(D, N, M, missing=True) as s:
+        s.synth(1234, 0.2)
+        Y = s.read_data()
+        assert 0.19 < np.isnan(Y).mean() < 0.21
+        s.init(W0, 1.0)
+        mu, W, s2 = np.zeros(D), W0.copy(), 1.0
+        est = None
+        for step in range(1, 3):
+            s.steps(1)
+            p = s.params()
+            mu, W, s2, mdw, dv, est = oppca.missed_step_vectorised(Y, mu, W, s2)
+            assert p["steps"] == step
+            assert rel(p["mu"], mu) < 1e-9, (step, rel(p["mu"], mu))
+            assert rel(p["W"], W) < 1e-9, (step, rel(p["W"], W))
+            assert abs(p["sigma2"] - s2) < 1e-9 * s2, (step, p["sigma2"], s2)
+            assert abs(p["max_dw"] - mdw) < 1e-9 * np.max(np.abs(W))
+        ll = s.loglik()
+        R = s.restored()
+    ll_ref = oppca.missed_loglik_vectorised(Y, mu, W, s2)
+    assert abs(ll - ll_ref) < 1e-9 * abs(ll_ref), (ll, ll_ref)
+    R_ref = oppca.missed_restore_literal(mu, W, s2, est["EX"])
+    assert rel(R, R_ref) < 1e-8, rel(R, R_ref)
+
+
+def test_masked_left_k_steps_done_and_mu():
+    N = 3000
+    rng = np.random.default_rng(12)
+    Y = rng.standard_normal((D, M)) @ rng.standard_normal((M, N)) + rng.standard_normal((D, 1)) + 0.5 * rng.standard_normal((D, N))
+    mask = rng.random((D, N)) < 0.2
+    mask[0] = False
+    Y = np.where(mask, np.nan, Y)
+    W0 = rng.standard_normal((D, M))
+    ref = oppca.em_steps_missed_vectorised(Y, W0, 1.0, ("left", 3))
+    with g.Session(D, N, M, missing=True) as s:
+        s.load_host(Y)
+        s.init(W0, 1.0)
+        done = s.run(g.Left(3))
+        p = s.params()
+    assert done == ref.steps_done == 4 and p["steps"] == 4
+    assert rel(p["W"], ref.W) < 1e-9
+    # mu' of the last step, recomputed by the oracle
+    mu, W, s2 = np.zeros(D), W0.copy(), 1.0
+    for _ in range(4):
+        mu, W, s2, _, _, _ = oppca.missed_step_vectorised(Y, mu, W, s2)
+    assert rel(p["mu"], mu) < 1e-9
+
+
+def test_gp_full_factor_n8192():
+    """n = 8192 = 64 panels of 128 (two-stream look-ahead, trailing updates over > 32 panels): the whole factor."""
+    n = 8192
+    rng = np.random.default_rng(2468)
+    X = rng.uniform(0, 30.0, (n, 2))
+    y = np.sin(X[:, 0]) + np.cos(X[:, 1]) + 0.1 * rng.standard_normal(n)
+    il2 = np.array([10.0, 10.0])
+    Lr, lmlr = ogp.gp_chol_lml(X, y, il2, 1.0, 5e-5)
+    L, lml, logdet = g.gp_chol_lml(X, y, il2, 1.0, 5e-5)
+    assert rel(L, Lr) < 1e-9, rel(L, Lr)
+    assert abs(lml - lmlr) < 1e-9 * abs(lmlr)
+    assert abs(logdet - 2.0 * np.sum(np.log(np.diag(Lr)))) < 1e-9 * abs(logdet)
+
+
+def test_gp_n32768_sampled_rows():
+    """BASELINE config 5 size.  The oracle cannot factor 32768^2 in seconds, so the factor is checked through the
+    identity it must satisfy, on sampled rows:  (L L^T)[r, :] = K(x_r, .) + jitter e_r  (kernel rows from the oracle),
+    and the log-determinant / LML through  logdet = 2 sum log L_ii,  lml = -1/2 |L^-1 y|^2 - 1/2 logdet - n/2 log 2pi
+    with L^-1 y recomputed on the host for the leading 2048 x 2048 block (forward substitution is prefix-closed)."""
+    n = 32768
+    rng = np.random.default_rng(2468)
+    X = rng.uniform(0, 60.0, (n, 2))
+    y = np.sin(X[:, 0]) + np.cos(X[:, 1]) + 0.1 * rng.standard_normal(n)
+    il2 = np.array([10.0, 10.0])
+    L, lml, logdet = g.gp_chol_lml(X, y, il2, 1.0, 5e-5)
+    assert np.isfinite(lml) and np.isfinite(logdet)
+    assert not np.any(np.triu(L[:512, :512], 1))
+    d = np.diag(L)
+    assert np.all(d > 0)
+    assert abs(logdet - 2.0 * np.sum(np.log(d))) < 1e-10 * abs(logdet)
+    rows = np.concatenate([[0, 1, 127, 128, 255, 256, 257, n - 1], rng.integers(0, n, 24)])
+    for r in rows:
+        krow = ogp.ard_kernel(X, X[r:r + 1], il2, 1.0)[0]          # K(x_r, x_j) for all j
+        krow[r] += 5e-5
+        got = L[r, :r + 1] @ L[:, :r + 1].T                          # (L L^T)[r, :]
+        assert np.max(np.abs(got - krow)) < 1e-11, (r, np.max(np.abs(got - krow)))
+    # prefix of the forward substitution and the LML identity
+    import scipy.linalg as sla
+    nb = 2048
+    Lr, _ = ogp.gp_chol_lml(X[:nb], y[:nb], il2, 1.0, 5e-5)
+    assert rel(L[:nb, :nb], Lr) < 1e-9
+    alpha = sla.solve_triangular(L, y, lower=True, check_finite=False)
+    lml_host = -0.5 * float(alpha @ alpha) - 0.5 * logdet - 0.5 * n * np.log(2 * np.pi)
+    assert abs(lml - lml_host) < 1e-9 * abs(lml_host), (lml, lml_host)
