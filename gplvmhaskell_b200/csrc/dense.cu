@@ -114,15 +114,26 @@ __global__ void __launch_bounds__(256) stats_gemm_kernel(const double* __restric
 // bit-identical total and the replicated update stays replicated.  A block publishes before it waits, so no rank can
 // block another.  Two buffers (step parity) suffice: a rank overwrites buffer k & 1 at step k + 2, after all of its
 // blocks have seen every peer's step k + 1 flags, which a peer raises only after its step-k kernel (and reads) finished.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, double* __restrict__ stats,
+// (partials and stats may alias: the in-place peer all-reduce of the masked statistics passes the same buffer)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* partials, double* stats,
                                                               int64_t S, int nparts, double* __restrict__ scal, PeerArgs pa) {
   if (scal && scal[S_DONE] != 0.0) return;
   __shared__ double part[8][33];
   const int o = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + o;
   double a = 0.0;
-  if (i < S)
-    for (int p = grp; p < nparts; p += 8) a += partials[(int64_t)p * S + i];
+  if (i < S) {
+    // the loads of 8 consecutive terms are issued together (L2 latency overlaps); the additions keep their order
+    int p = grp;
+    for (; p + 56 < nparts; p += 64) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(&partials[(int64_t)(p + 8 * u) * S + i]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; p < nparts; p += 8) a += __ldcg(&partials[(int64_t)p * S + i]);
+  }
   part[grp][o] = a;
   __syncthreads();
   double t = 0.0;
@@ -339,77 +350,100 @@ __global__ void __launch_bounds__(256) dense_update_kernel(Par p, const double* 
   dense_prep_block(p, sm);  // parameters for the next E-step (also what the LL pass needs)
 }
 
-// Fast path of the replicated update for MP = 16 (the fused-kernel shape): both 16 x 16 problems are inverted in
-// registers by one half-warp each (sweep_inverse16), every per-feature product is statically unrolled, the new W is
-// kept in shared memory for W^T W.  Follows the reference literally: W' = XEz . inv(Ezz) (PPCA.hs:74); the third term
-// |W' U^T|_F^2 with U = chol(Ezz) (PPCA.hs:75-76,79) equals sum_d w'_d^T Ezz w'_d and is evaluated in that form.
-// Also computes the next E-step's M^-1 = (s2' I + W'^T W')^-1, log det and A = W' M^-1 (dense_prep_block).
-// sm: Ezz 256 | Einv 256 | Mm 256 | Mi 256 | red 40 | Ws D x 16
+// In-place inverse of the symmetric positive definite 16 x 16 matrix A (shared memory, row-major) by ALL 256 threads of
+// the block: 16 symmetric sweeps (see sweep_inverse16), thread (i, l) owns entry A[i][l].  Returns (in every thread) whether
+// every pivot was positive; det = product of the pivots.  A plain loop: the code stays a few hundred instructions (the
+// fully unrolled register version made the single-CTA update kernel 13 000 instructions = 208 KB, which streamed from L2
+// on every launch and cost ~25 of its 36 microseconds).
+__device__ __forceinline__ bool block_sweep_inverse16(double* A, int tid, double& det) {
+  const int i = tid >> 4, l = tid & 15;
+  bool ok = true;
+  det = 1.0;
+#pragma unroll 1
+  for (int k = 0; k < 16; ++k) {
+    const double pk = A[k * 16 + k], aik = A[i * 16 + k], akl = A[k * 16 + l], ail = A[tid];
+    ok = ok && (pk > 0.0);
+    det *= pk;
+    const double d = 1.0 / pk;
+    __syncthreads();
+    double v;
+    if (i == k) v = (l == k) ? -d : akl * d;
+    else v = (l == k) ? aik * d : fma(-aik * d, akl, ail);
+    A[tid] = v;
+    __syncthreads();
+  }
+  A[tid] = -A[tid];
+  __syncthreads();
+  return ok;
+}
+
+// Fast path of the replicated update for MP = 16 (the fused-kernel shape).  Follows the reference literally:
+// W' = XEz . inv(Ezz) (PPCA.hs:74); the third term |W' U^T|_F^2 with U = chol(Ezz) (PPCA.hs:75-76,79) equals
+// sum_d w'_d^T Ezz w'_d and is evaluated in that form.  Also computes the next E-step's M^-1 = (s2' I + W'^T W')^-1,
+// log det and A = W' M^-1 (dense_prep_block).  Loops over the latent index stay rolled (small code, see above); the
+// operands of the inner, unrolled loops are rows of the 16 x 16 matrices in shared memory.
+// Round-2 measurements (N = 2^20 per GPU, the 8-GPU shard): fully unrolled register version 13 008 instructions, 32-35 us;
+// this version 1 544 instructions, 27 us; a 1024-thread variant (4 threads per feature) 31 us -- what is left is a chain of
+// short dependent phases on one SM, not instruction fetch and not the arithmetic.
+// sm: Ezz 256 | Einv 256 | Mi 256 | red 40 | Ws D x 17 | Bs D x 17
 __global__ void __launch_bounds__(256, 1) dense_update16_kernel(Par p, const double* __restrict__ stats) {
   extern __shared__ double sm[];
   if (p.scal[S_DONE] != 0.0) return;
   constexpr int MP = 16;
+  constexpr int WSP = 17;   // pitch of the per-feature rows in shared memory: one feature per thread => conflict-free
   const int D = p.D, tid = threadIdx.x;
   double* Ezz = sm;
   double* Einv = sm + 256;
-  double* Mm = sm + 512;
-  double* Mi = sm + 768;
-  double* red = sm + 1024;
-  double* Ws = sm + 1024 + 40;
-  __shared__ int okflag;
+  double* Mi = sm + 512;
+  double* red = sm + 768;
+  double* Ws = sm + 768 + 40;
+  double* Bs = Ws + (size_t)D * WSP;   // XEz staged once, coalesced (a rolled loop over global loads would serialise their latency)
   const double* XEz = stats;
   const double* EE = stats + (int64_t)D * MP;
   const double s2 = p.scal[S_SIGMA2];
   const double Nd = (double)p.N;
-  Ezz[tid] = Nd * s2 * p.Minv[tid] + EE[tid];
-  if (tid == 0) okflag = 1;
-  __syncthreads();
-  if (tid < 32) {   // lanes 0-15 invert Ezz (lanes 16-31 run the same code on the same matrix: full-warp shuffles)
-    const int c = tid & 15;
-    double m[16];
-#pragma unroll
-    for (int a = 0; a < 16; ++a) m[a] = Ezz[a * 16 + c];
-    bool ok;
-    double det;
-    sweep_inverse16(m, c, ok, det);
-    if (tid < 16) {
-#pragma unroll
-      for (int a = 0; a < 16; ++a) Einv[a * 16 + c] = m[a];
-      if (!ok && c == 0) okflag = 0;
-    }
+  {
+    const double e = Nd * s2 * p.Minv[tid] + EE[tid];
+    for (int i = tid; i < D * 16; i += 256) Bs[(i >> 4) * WSP + (i & 15)] = XEz[i];
+    Ezz[tid] = e;
+    Einv[tid] = e;
   }
   __syncthreads();
+  double det;
+  const bool ok1 = block_sweep_inverse16(Einv, tid, det);
   double second = 0.0, third = 0.0, maxdw = 0.0;
-  // volatile views: keep the 16 x 16 operands in shared memory (the compiler would otherwise hoist all 512 loads out
-  // of the feature loop and spill them)
-  const volatile double* Ev = Einv;
-  const volatile double* Zv = Ezz;
-  const volatile double* Miv = Mi;
   for (int d = tid; d < D; d += 256) {
-    double b[16], x[16];
+    const double* b = Bs + d * WSP;
+    double x[16];
 #pragma unroll
-    for (int a = 0; a < 16; ++a) b[a] = XEz[(int64_t)d * MP + a];
+    for (int a = 0; a < 16; ++a) x[a] = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {   // row vector times inv(Ezz)
+      const double bk = b[k];
+      const double* er = Einv + k * 16;
+#pragma unroll
+      for (int a = 0; a < 16; ++a) x[a] = fma(bk, er[a], x[a]);
+    }
+    double* wrow = p.W + (int64_t)d * MP;
 #pragma unroll
     for (int a = 0; a < 16; ++a) {
-      double t = 0.0;
+      maxdw = fmax(maxdw, fabs(wrow[a] - x[a]));
+      wrow[a] = x[a];
+      Ws[d * WSP + a] = x[a];
+    }
+    double y[16];   // Ezz w'_d
 #pragma unroll
-      for (int k = 0; k < 16; ++k) t = fma(b[k], Ev[k * 16 + a], t);   // row vector times inv(Ezz)
-      x[a] = t;
+    for (int a = 0; a < 16; ++a) y[a] = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+      const double xk = Ws[d * WSP + k];   // own row: written by this thread
+      second = fma(xk, b[k], second);
+      const double* zr = Ezz + k * 16;
+#pragma unroll
+      for (int a = 0; a < 16; ++a) y[a] = fma(zr[a], xk, y[a]);
     }
 #pragma unroll
-    for (int a = 0; a < 16; ++a) {
-      double t = 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) t = fma(Zv[a * 16 + k], x[k], t);
-      third = fma(x[a], t, third);
-      second = fma(x[a], b[a], second);
-      maxdw = fmax(maxdw, fabs(p.W[(int64_t)d * MP + a] - x[a]));
-    }
-#pragma unroll
-    for (int a = 0; a < 16; ++a) {
-      p.W[(int64_t)d * MP + a] = x[a];
-      Ws[d * 16 + a] = x[a];
-    }
+    for (int a = 0; a < 16; ++a) third = fma(x[a], y[a], third);
   }
   second = 2.0 * block_sum(second, red);
   third = block_sum(third, red);
@@ -422,54 +456,45 @@ __global__ void __launch_bounds__(256, 1) dense_update16_kernel(Par p, const dou
     p.scal[S_DVAR] = dvar;
     p.scal[S_MAXDW] = maxdw;
     p.scal[S_STEPS] += 1.0;
-    if (!okflag || !(news2 > 0.0)) set_err(p.scal, 1.0);
+    if (!ok1 || !(news2 > 0.0)) set_err(p.scal, 1.0);
     if (p.scal[S_USETOL] != 0.0 && !(fmax(dvar, maxdw) > p.scal[S_TOL])) p.scal[S_DONE] = 1.0;
   }
   {  // M = s2' I + W'^T W'
     const int a = tid >> 4, b = tid & 15;
-    double t0 = 0.0, t1 = 0.0;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
     int d = 0;
-    for (; d + 1 < D; d += 2) {
-      t0 = fma(Ws[d * 16 + a], Ws[d * 16 + b], t0);
-      t1 = fma(Ws[(d + 1) * 16 + a], Ws[(d + 1) * 16 + b], t1);
+#pragma unroll 2
+    for (; d + 3 < D; d += 4) {
+      t0 = fma(Ws[d * WSP + a], Ws[d * WSP + b], t0);
+      t1 = fma(Ws[(d + 1) * WSP + a], Ws[(d + 1) * WSP + b], t1);
+      t2 = fma(Ws[(d + 2) * WSP + a], Ws[(d + 2) * WSP + b], t2);
+      t3 = fma(Ws[(d + 3) * WSP + a], Ws[(d + 3) * WSP + b], t3);
     }
-    if (d < D) t0 = fma(Ws[d * 16 + a], Ws[d * 16 + b], t0);
-    Mm[tid] = (t0 + t1) + ((a == b) ? news2 : 0.0);
+    for (; d < D; ++d) t0 = fma(Ws[d * WSP + a], Ws[d * WSP + b], t0);
+    Mi[tid] = ((t0 + t1) + (t2 + t3)) + ((a == b) ? news2 : 0.0);
   }
   __syncthreads();
-  if (tid < 32) {
-    const int c = tid & 15;
-    double m[16];
-#pragma unroll
-    for (int a = 0; a < 16; ++a) m[a] = Mm[a * 16 + c];
-    bool ok;
-    double det;
-    sweep_inverse16(m, c, ok, det);
-    if (tid < 16) {
-#pragma unroll
-      for (int a = 0; a < 16; ++a) {
-        Mi[a * 16 + c] = m[a];
-        p.Minv[a * 16 + c] = m[a];
-      }
-      if (c == 0) {
-        // log det over the first M pivots only matters when M < 16 (padded columns contribute log s2 each)
-        p.scal[S_LOGDETM] = log(det) - (double)(16 - p.M) * log(news2);
-        if (!ok) set_err(p.scal, 1.0);
-      }
-    }
+  const bool ok2 = block_sweep_inverse16(Mi, tid, det);
+  p.Minv[tid] = Mi[tid];
+  if (tid == 0) {
+    // log det over the first M pivots only matters when M < 16 (padded columns contribute log s2 each)
+    p.scal[S_LOGDETM] = log(det) - (double)(16 - p.M) * log(news2);
+    if (!ok2) set_err(p.scal, 1.0);
   }
-  __syncthreads();
   for (int d = tid; d < D; d += 256) {
-    double w[16];
+    double acc[16];
 #pragma unroll
-    for (int a = 0; a < 16; ++a) w[a] = Ws[d * 16 + a];
+    for (int b = 0; b < 16; ++b) acc[b] = 0.0;
+#pragma unroll 1
+    for (int a = 0; a < 16; ++a) {
+      const double wa = Ws[d * WSP + a];
+      const double* mr = Mi + a * 16;
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
-      double t = 0.0;
-#pragma unroll
-      for (int a = 0; a < 16; ++a) t = fma(w[a], Miv[a * 16 + b], t);
-      p.A[(int64_t)d * MP + b] = t;
+      for (int b = 0; b < 16; ++b) acc[b] = fma(wa, mr[b], acc[b]);
     }
+    double* arow = p.A + (int64_t)d * MP;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) arow[b] = acc[b];
   }
 }
 
@@ -604,34 +629,53 @@ static int dense_stats_pass(gplvm_ppca_session* s, ShardState& sh, const double*
   return launch_stats_gemm(sh, ROWS_DENSE, D, R, R, MP, MP, sh.Ez, MP, MP, nullptr, 0, s->S, sh.stats);
 }
 
+// arguments of the next exchange over peer memory (session_setup_p2p succeeded): one epoch per exchange, two buffers
+static void next_peer_args(gplvm_ppca_session* s) {
+  s->xchg_epoch += 1;
+  for (ShardState& sh : s->sh) {
+    sh.peer_args.peers = sh.peers_dev;
+    sh.peer_args.world = ctx().world;
+    sh.peer_args.rank = ctx().multiproc ? ctx().rank : (int)(&sh - &s->sh[0]);
+    sh.peer_args.parity = (int)(s->xchg_epoch & 1);
+    sh.peer_args.epoch = s->xchg_epoch;
+    sh.peer_args.S = (long long)s->S;
+  }
+}
+
+// In-place all-reduce of sh.stats (s->S doubles) over NVLink peer memory: the reduction kernel with a single "partial"
+// (the local statistics themselves) publishes, waits for the peers' flags and adds the ranks in rank order.
+int session_peer_allreduce_stats(gplvm_ppca_session* s) {
+  if (!s->p2p) return fail(GPLVM_ERR_STATE, "peer exchange is not set up");
+  next_peer_args(s);
+  for (ShardState& sh : s->sh) {
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    GP_LAUNCH(reduce_partials_kernel, (unsigned)ceil_div(s->S, 32), 256, 0, sh.st, sh.stats, sh.stats, s->S, 1, sh.par.scal, sh.peer_args);
+    sh.peer_args.peers = nullptr;
+  }
+  return GPLVM_OK;
+}
+
 int dense_enqueue_step(gplvm_ppca_session* s) {
   const bool p2p_step = s->p2p;
-  if (p2p_step) s->xchg_epoch += 1;
+  if (p2p_step) next_peer_args(s);
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (sh.evk0) CUDA_TRY(cudaEventRecord(sh.evk0, sh.st));
     seg_mark(sh, 0);
-    if (p2p_step) {
-      sh.peer_args.peers = sh.peers_dev;
-      sh.peer_args.world = ctx().world;
-      sh.peer_args.rank = ctx().multiproc ? ctx().rank : (int)(&sh - &s->sh[0]);
-      sh.peer_args.parity = (int)(s->xchg_epoch & 1);
-      sh.peer_args.epoch = s->xchg_epoch;
-      sh.peer_args.S = (long long)s->S;
-    }
+    if (!p2p_step) sh.peer_args.peers = nullptr;
     GP_TRY(dense_stats_pass(s, sh, sh.par.A, true));
     sh.peer_args.peers = nullptr;
     if (sh.evk1) CUDA_TRY(cudaEventRecord(sh.evk1, sh.st));
   }
   const size_t smem = sizeof(double) * (2 * s->MP * s->MP + 64);
-  const bool fast16 = (s->MP == 16 && s->D <= 1024);
+  const bool fast16 = (s->MP == 16 && s->D <= 512);
   if (!s->p2p) GP_TRY(session_allreduce_stats(s, s->S));
-  const size_t smem16 = sizeof(double) * (1024 + 40 + (size_t)s->D * 16);
+  const size_t smem16 = sizeof(double) * (768 + 40 + (size_t)s->D * 34);
   static bool attr_done[64] = {};
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (fast16 && !attr_done[sh.dev & 63]) {
-      CUDA_TRY(cudaFuncSetAttribute(dense_update16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(dense_update16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       attr_done[sh.dev & 63] = true;
     }
     seg_mark(sh, 2);

@@ -334,14 +334,10 @@ __global__ void __launch_bounds__(256, MINB) masked_miss_sums_kernel(const doubl
 
 // per-feature update, one warp per feature.  stats layout (all-reduced):
 //   [miss_d = (vech G^miss_d | S1^miss_d) : D x eas] [tot = (vech sum A | sum ez) : eas] [S2_d : D x M]
-__global__ void __launch_bounds__(EW * 32) masked_update_kernel(Par p, const double* __restrict__ stats, double* __restrict__ scratch) {
-  if (p.scal[S_DONE] != 0.0) return;
-  extern __shared__ double sm[];
+// update of one feature by one warp; leaves the new w_d in the warp's `r` slot of shared memory (sm + 2 M^2)
+__device__ __forceinline__ void masked_update_feature(const Par& p, const double* __restrict__ stats, double* __restrict__ scratch,
+                                                      double* G, int d, int lane) {
   const int M = p.M, NV = p.NV, D = p.D;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int d = blockIdx.x * EW + w;
-  if (d >= D) return;
-  double* G = sm + (size_t)w * (2 * M * M + 3 * M);
   double* G0 = G + M * M;
   double* r = G0 + M * M;
   double* wold = r + M;
@@ -401,6 +397,29 @@ __global__ void __launch_bounds__(EW * 32) masked_update_kernel(Par p, const dou
   }
 }
 
+
+// wtw_part[blockIdx.x][M x M] receives the block's share of W'^T W' (summed in fixed order by the finalize kernel).
+__global__ void __launch_bounds__(EW * 32) masked_update_kernel(Par p, const double* __restrict__ stats, double* __restrict__ scratch,
+                                                               double* __restrict__ wtw_part) {
+  if (p.scal[S_DONE] != 0.0) return;
+  extern __shared__ double sm[];
+  const int M = p.M, NV = p.NV, D = p.D;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int d = blockIdx.x * EW + w;
+  if (d < D) masked_update_feature(p, stats, scratch, sm + (size_t)w * (2 * M * M + 3 * M), d, lane);
+  __syncthreads();
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int a = e / M, c = e % M;
+    double t = 0.0;
+    for (int w2 = 0; w2 < EW; ++w2) {
+      if (blockIdx.x * EW + w2 >= D) break;
+      const double* wn = sm + (size_t)w2 * (2 * M * M + 3 * M) + 2 * M * M;   // this warp's new w_d (the solved r)
+      t = fma(wn[a], wn[c], t);
+    }
+    wtw_part[(size_t)blockIdx.x * M * M + e] = t;
+  }
+}
+
 // C0 = s2 I + W^T W into p.Minv (single CTA)
 __device__ void masked_prep_block(const Par& p) {
   const int D = p.D, M = p.M;
@@ -415,7 +434,8 @@ __device__ void masked_prep_block(const Par& p) {
 }
 __global__ void __launch_bounds__(256) masked_prep_kernel(Par p) { masked_prep_block(p); }
 
-__global__ void __launch_bounds__(256) masked_finalize_kernel(Par p, const double* __restrict__ stats, const double* __restrict__ scratch) {
+__global__ void __launch_bounds__(256) masked_finalize_kernel(Par p, const double* __restrict__ stats, const double* __restrict__ scratch,
+                                                              const double* __restrict__ wtw_part, int nblocks) {
   if (p.scal[S_DONE] != 0.0) return;
   __shared__ double red[40];
   const int D = p.D, M = p.M, NV = p.NV;
@@ -442,8 +462,13 @@ __global__ void __launch_bounds__(256) masked_finalize_kernel(Par p, const doubl
     if (p.scal[S_USETOL] != 0.0 && !(fmax(dvar, m) > p.scal[S_TOL])) p.scal[S_DONE] = 1.0;
   }
   __syncthreads();
-  __threadfence_block();
-  masked_prep_block(p);
+  // C0 = s2' I + W'^T W' for the next E-step, from the update kernel's per-block partial Gram matrices (fixed order)
+  const double news2 = p.scal[S_SIGMA2];
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += wtw_part[(size_t)b * M * M + e];
+    p.Minv[e] = t + ((e / M == e % M) ? news2 : 0.0);
+  }
 }
 
 // data constants: stats = [n_d | sy_d | syy_d] (all-reduced)
@@ -644,12 +669,15 @@ int masked_enqueue_step(gplvm_ppca_session* s) {
     }
     if (sh.evk1) CUDA_TRY(cudaEventRecord(sh.evk1, sh.st));
   }
-  GP_TRY(session_allreduce_stats(s, s->S));
+  // one combination of the packed statistics per step: over NVLink peer memory when the mappings exist, else NCCL
+  if (s->p2p) GP_TRY(session_peer_allreduce_stats(s));
+  else GP_TRY(session_allreduce_stats(s, s->S));
   for (ShardState& sh : s->sh) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     if (s->use_dmma) seg_mark(sh, 5);
-    GP_LAUNCH(masked_update_kernel, (unsigned)ceil_div(D, EW), EW * 32, smem, sh.st, sh.par, sh.stats, sh.scratch);
-    GP_LAUNCH(masked_finalize_kernel, 1, 256, 0, sh.st, sh.par, sh.stats, sh.scratch);
+    double* wtw_part = sh.scratch + (size_t)8 * D;   // ceil(D / EW) x M x M (session_create sizes the scratch block)
+    GP_LAUNCH(masked_update_kernel, (unsigned)ceil_div(D, EW), EW * 32, smem, sh.st, sh.par, sh.stats, sh.scratch, wtw_part);
+    GP_LAUNCH(masked_finalize_kernel, 1, 256, 0, sh.st, sh.par, sh.stats, sh.scratch, wtw_part, (int)ceil_div(D, EW));
     if (s->use_dmma) seg_mark(sh, 6);
   }
   return GPLVM_OK;

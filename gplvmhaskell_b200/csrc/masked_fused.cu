@@ -25,79 +25,105 @@ namespace {
 constexpr int MF = 16;
 constexpr int NVF = MF * (MF + 1) / 2;   // 136
 constexpr int EASF = NVF + MF;           // 152
-constexpr int WP = 18;                   // pitch (doubles) of the W rows in shared memory: spreads gathered rows over the banks
+// Pitch (doubles) of the W rows in shared memory: spreads the gathered rows over the banks.  (A residue-bucketed gather --
+// lane t only gathers features d = t mod 4 from rows of pitch 20, which makes every gather bank-conflict free -- was built
+// and measured in round 2: shared-memory load wavefronts -37 %, conflicts -96 %, but +21 % k-steps and +30 % instructions:
+// 16.2 ms against 12.6 ms at N = 2^23.  The kernel is bound by issue latency at 8 warps per SM, not by the data pipe.)
+constexpr int WP = 18;
+constexpr int EAP = 156;                 // pitch (doubles) of the staged [vech A | ez] rows: 8 observations x 4 lanes bank-disjoint
 
 // LL = false: writes EA[n] = [vech A_i | ez_i].   LL = true: accumulates the per-observation likelihood terms
 //   cnt log 2pi + (cnt - M) log s2 + log det M_i + (yy_i - b_i . ez_i) / s2      into partials[blockIdx.x].
 //
-// One warp handles 8 observations at a time.  During the sweeps a QUAD of lanes owns one observation: lane j of the
-// quad holds columns j, j+4, j+8, j+12 of the symmetric 16 x 16 matrix (4 x 16 registers), so one 64-bit shuffle
-// moves a column entry for 8 observations at once (4x fewer shuffle wavefronts per observation than a half-warp
-// per observation -- the shared-memory/shuffle data pipe is what bounds this kernel).
-constexpr int LPR = 8;                          // lanes per observation during the sweeps (4: quad, 8: oct)
-constexpr int CPL = MF / LPR;                   // matrix columns per lane
-constexpr int SOLVE_ROWS = 32 / LPR;            // observations per warp
+// One warp handles ROWS = 32 / LPR observations at a time.  During the sweeps a group of LPR lanes owns one
+// observation: lane j of the group holds columns j, j + LPR, ... of the symmetric 16 x 16 matrix (CPL x 16 registers),
+// so one 64-bit shuffle moves a column entry for ROWS observations at once -- the shared-memory/shuffle data pipe is what
+// bounds this kernel: 256 column entries travel per observation, i.e. 512 / ROWS shuffle wavefronts.
+//   LPR = 8: 4 observations per warp, 32 matrix registers per lane, 2 CTAs per SM;
+//   LPR = 4: 8 observations per warp, 64 matrix registers per lane, 1 CTA per SM, half the shuffle wavefronts.
+// The Gram matrices are built one observation at a time (own k-loop bound: no padding to the longest list of the warp)
+// and staged through shared memory into the sweep layout; [vech A | ez] rows leave through the same staging area as
+// coalesced 128-bit stores (the ROWS rows of a warp are contiguous in HBM).
 constexpr int SOLVE_WARPS = 8;                  // warps per CTA
-constexpr int SOLVE_MINB = (LPR == 8) ? 2 : 1;  // CTAs per SM (register budget: CPL x 16 doubles per lane for the matrix)
-// Issuing DMMA (Gram) and DFMA (sweep) work from one SM at the same time costs throughput (tools/fp64_mix.cu: 37 / 34
-// TFLOP/s alone, 23 TFLOP/s mixed), but separating the phases with CTA barriers (1 CTA of 16 warps) measured slower
-// (1.96 ms vs 1.72 ms per 2^20 observations) than letting two 8-warp CTAs drift: kept off.
-constexpr bool SOLVE_PHASED = false;
 constexpr int MS_STRIDE = MF * 17 + 4;          // doubles per staged matrix; +4 spreads the lane groups over the banks
 
-template <int DD, bool LL>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ yy,
-                                                             const uint32_t* __restrict__ mbits, int64_t n_obs, Par p,
-                                                             double* __restrict__ EA, double* __restrict__ partials,
-                                                             uint32_t* __restrict__ eamax) {
+template <int LPR>
+struct SolveCfg {
+  static constexpr int WPS = WP;                 // pitch of the W rows
+  static constexpr int NZ = 1;                   // zero rows appended to W (list padding)
+  static constexpr int CPL = MF / LPR;           // matrix columns per lane
+  static constexpr int ROWS = 32 / LPR;          // observations per warp
+  static constexpr int MINB = (LPR == 8) ? 2 : 1;
+  // LPR = 4: the index lists get their own region (a matrix is staged while later lists are still needed);
+  // LPR = 8: they alias the staging area (two CTAs must fit in one SM) and the Gram fragments wait in registers
+  static constexpr bool LIST_SEP = ROWS > 4;
+  static __host__ __device__ constexpr int warp_doubles(int DD) { return ROWS * MS_STRIDE + (LIST_SEP ? ROWS * DD / 4 : 0); }
+  static __host__ __device__ constexpr int smem_bytes(int DD) { return ((DD + NZ) * WPS + SOLVE_WARPS * warp_doubles(DD)) * (int)sizeof(double); }
+};
+
+template <int DD, bool LL, int LPR>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32, SolveCfg<LPR>::MINB)
+masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ yy, const uint32_t* __restrict__ mbits, int64_t n_obs,
+                    Par p, double* __restrict__ EA, double* __restrict__ partials, uint32_t* __restrict__ eamax) {
+  using SC = SolveCfg<LPR>;
+  constexpr int CPL = SC::CPL, ROWS = SC::ROWS, WPS = SC::WPS, NZ = SC::NZ;
   constexpr int WPRT = DD / 32;
   static_assert(WPRT <= 8, "mask words per observation");
+  static_assert(SC::LIST_SEP || ROWS * MS_STRIDE * 8 >= ROWS * DD * 2, "index lists must fit in the staging area");
+  static_assert(MS_STRIDE >= EAP && EAP >= EASF, "[vech A | ez] rows must fit in the staging area");
+  static_assert(DD % 4 == 0, "list region size");
   if (!LL && p.scal[S_DONE] != 0.0) return;
-  extern __shared__ double sm[];
-  double* Ws = sm;                               // (DD + 1) x WP : rows of W, pitch 18 doubles; row DD = 0 (list padding)
-  double* C0s = Ws + (DD + 1) * WP;              // 16 x 16 : s2 I + W^T W  (kept in p.Minv by the masked prep kernel)
-  double* Msm = C0s + MF * MF;                   // per warp: SOLVE_ROWS staged W_miss^T W_miss matrices; the index
-  uint16_t* lists = reinterpret_cast<uint16_t*>(Msm);  // lists (SOLVE_ROWS x DD uint16) alias them (dead after the Gram loop)
+  extern __shared__ __align__(16) double sm[];
+  double* Ws = sm;                               // (DD + NZ) x WPS : rows of W; rows DD .. = 0 (list / bucket padding)
+  double* Msm = Ws + (DD + NZ) * WPS;            // per warp: ROWS staged matrices [+ index lists]
   __shared__ double red[40];
-  for (int e = threadIdx.x; e < (DD + 1) * MF; e += blockDim.x) {
+  for (int e = threadIdx.x; e < (DD + NZ) * MF; e += blockDim.x) {
     const int d = e >> 4, a = e & 15;
-    Ws[d * WP + a] = (d < DD) ? p.W[e] : 0.0;
+    Ws[d * WPS + a] = (d < DD) ? p.W[e] : 0.0;
   }
-  for (int e = threadIdx.x; e < MF * MF; e += blockDim.x) C0s[e] = p.Minv[e];
   __syncthreads();
   const double s2 = p.scal[S_SIGMA2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;         // MMA fragment coordinates
   const int rw = lane / LPR, j = lane % LPR;     // sweep coordinates: observation within the warp, lane within its group
-  double* Mw = Msm + warp * (SOLVE_ROWS * MS_STRIDE);
-  uint16_t* lst = reinterpret_cast<uint16_t*>(Mw);
-  static_assert(SOLVE_ROWS * MS_STRIDE * 8 >= SOLVE_ROWS * 256 * 2, "index lists must fit in the staging area");
+  constexpr int WARP_DOUBLES = SC::warp_doubles(DD);
+  double* Mw = Msm + warp * WARP_DOUBLES;
+  // C0 = s2 I + W^T W (kept in p.Minv by the masked prep kernel) at this lane's C-fragment positions (tiles 00, 01, 11):
+  // the staged matrix is C0 - Gram
+  double c00[2], c01[2], c11[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    c00[q] = p.Minv[g * MF + 2 * t + q];
+    c01[q] = p.Minv[g * MF + 8 + 2 * t + q];
+    c11[q] = p.Minv[(8 + g) * MF + 8 + 2 * t + q];
+  }
+  uint16_t* lst = reinterpret_cast<uint16_t*>(SC::LIST_SEP ? Mw + ROWS * MS_STRIDE : Mw);   // ROWS x DD uint16
   constexpr unsigned FULL = 0xffffffffu;
   // The trip count depends on blockIdx only, so the compiler can see that every warp stays converged around the
   // shuffles (a warp whose observations lie past the end recomputes the last one and stores nothing).
-  const int64_t cta0 = (int64_t)blockIdx.x * (SOLVE_WARPS * SOLVE_ROWS);
-  const int64_t stride = (int64_t)gridDim.x * (SOLVE_WARPS * SOLVE_ROWS);
+  const int64_t cta0 = (int64_t)blockIdx.x * (SOLVE_WARPS * ROWS);
+  const int64_t stride = (int64_t)gridDim.x * (SOLVE_WARPS * ROWS);
   const int64_t iters = (n_obs > cta0) ? (n_obs - cta0 + stride - 1) / stride : 0;
   double llacc = 0.0;
   uint32_t mxa = 0u, mxe = 0u;   // high words of the largest |vech A| and |ez| entries written (fixed-point scale, masked_fx.cuh)
   const double log2pi = 1.8378770664093453, logs2 = LL ? log(s2) : 0.0;
 
   for (int64_t it = 0; it < iters; ++it) {
-    const int64_t nb = cta0 + it * stride + warp * SOLVE_ROWS;   // first observation of this warp
-    // ---- (a) compact the missing-feature indices of the 8 observations ---------------------------------------
+    const int64_t nb = cta0 + it * stride + warp * ROWS;   // first observation of this warp
+    // ---- (a) compact the missing-feature indices of the ROWS observations ----------------------------------------
     uint32_t mwa = 0u, mwb = 0u;   // lane l: word (l & 7) of observation nb + (l >> 3) [+ 4]
     if ((lane & 7) < WPRT) {
       const int64_t na = min(nb + (lane >> 3), n_obs - 1);
       mwa = mbits[na * WPRT + (lane & 7)];
-      if (SOLVE_ROWS > 4) {
+      if (ROWS > 4) {
         const int64_t nc = min(nb + 4 + (lane >> 3), n_obs - 1);
         mwb = mbits[nc * WPRT + (lane & 7)];
       }
     }
-    int cnt[SOLVE_ROWS];
+    int cnt[ROWS];    // missing features of observation r
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int r = 0; r < SOLVE_ROWS; ++r) {
+    for (int r = 0; r < ROWS; ++r) {
       int cr = 0;
 #pragma unroll
       for (int wd = 0; wd < WPRT; ++wd) {
@@ -107,66 +133,82 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_ker
       }
       cnt[r] = cr;
     }
-    int cmax = 0;
-#pragma unroll
-    for (int r = 0; r < SOLVE_ROWS; ++r) cmax = max(cmax, cnt[r]);
-    const int nks = (cmax + 3) >> 2;
-#pragma unroll
-    for (int r = 0; r < SOLVE_ROWS; ++r)
-      for (int e = cnt[r] + lane; e < nks * 4; e += 32) lst[r * DD + e] = (uint16_t)DD;   // pad with the zero row of Ws
     __syncwarp();
-    if (SOLVE_PHASED) __syncthreads();
-    // ---- (b) K-compacted Gram matrices W_miss^T W_miss on the tensor cores (tiles 00, 01, 11 per observation) ----
-    {
-      double g00[SOLVE_ROWS][2], g01[SOLVE_ROWS][2], g11[SOLVE_ROWS][2];
+    // ---- (b) K-compacted Gram matrices W_miss^T W_miss on the tensor cores (tiles 00, 01, 11), one observation at a
+    //          time with its own loop bound; the last k-step is completed with the zero row of Ws ------------------------
+    double stash[SC::LIST_SEP ? 1 : ROWS][6];
 #pragma unroll
-      for (int r = 0; r < SOLVE_ROWS; ++r) g00[r][0] = g00[r][1] = g01[r][0] = g01[r][1] = g11[r][0] = g11[r][1] = 0.0;
-      for (int ks = 0; ks < nks; ++ks) {
-#pragma unroll
-        for (int r = 0; r < SOLVE_ROWS; ++r) {
-          const int d = lst[r * DD + ks * 4 + t];
-          const double f0 = Ws[d * WP + g], f1 = Ws[d * WP + 8 + g];
-          dmma(g00[r], f0, f0);
-          dmma(g01[r], f0, f1);
-          dmma(g11[r], f1, f1);
-        }
+    for (int r = 0; r < ROWS; ++r) {
+      double g00[2] = {0.0, 0.0}, g01[2] = {0.0, 0.0}, g11[2] = {0.0, 0.0};
+      const int cr = cnt[r];
+      const int nfull = cr >> 2;
+      const uint16_t* lr = lst + r * DD;
+#pragma unroll 4
+      for (int ks = 0; ks < nfull; ++ks) {
+        const int d = lr[ks * 4 + t];
+        const double f0 = Ws[d * WPS + g], f1 = Ws[d * WPS + 8 + g];
+        dmma(g00, f0, f0);
+        dmma(g01, f0, f1);
+        dmma(g11, f1, f1);
       }
-      __syncwarp();   // the index lists (aliased by the staging area) are dead from here on
-#pragma unroll
-      for (int r = 0; r < SOLVE_ROWS; ++r) {
+      if (cr & 3) {   // warp-uniform: the last k-step is completed with the zero row of Ws
+        const int e = nfull * 4 + t;
+        const int d = (e < cr) ? (int)lr[e] : DD;
+        const double f0 = Ws[d * WPS + g], f1 = Ws[d * WPS + 8 + g];
+        dmma(g00, f0, f0);
+        dmma(g01, f0, f1);
+        dmma(g11, f1, f1);
+      }
+      if constexpr (SC::LIST_SEP) {
         double* Mh = Mw + r * MS_STRIDE;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          Mh[g * 17 + 2 * t + q] = g00[r][q];
-          Mh[g * 17 + 8 + 2 * t + q] = g01[r][q];
-          Mh[(8 + 2 * t + q) * 17 + g] = g01[r][q];
-          Mh[(8 + g) * 17 + 8 + 2 * t + q] = g11[r][q];
+          Mh[g * 17 + 2 * t + q] = c00[q] - g00[q];
+          Mh[g * 17 + 8 + 2 * t + q] = c01[q] - g01[q];
+          Mh[(8 + 2 * t + q) * 17 + g] = c01[q] - g01[q];
+          Mh[(8 + g) * 17 + 8 + 2 * t + q] = c11[q] - g11[q];
+        }
+      } else {
+        stash[r][0] = c00[0] - g00[0]; stash[r][1] = c00[1] - g00[1]; stash[r][2] = c01[0] - g01[0];
+        stash[r][3] = c01[1] - g01[1]; stash[r][4] = c11[0] - g11[0]; stash[r][5] = c11[1] - g11[1];
+      }
+    }
+    if constexpr (!SC::LIST_SEP) {
+      __syncwarp();   // the index lists (aliased by the staging area) are dead from here on
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        double* Mh = Mw + r * MS_STRIDE;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          Mh[g * 17 + 2 * t + q] = stash[r][q];
+          Mh[g * 17 + 8 + 2 * t + q] = stash[r][2 + q];
+          Mh[(8 + 2 * t + q) * 17 + g] = stash[r][2 + q];
+          Mh[(8 + g) * 17 + 8 + 2 * t + q] = stash[r][4 + q];
         }
       }
     }
     __syncwarp();
-    if (SOLVE_PHASED) __syncthreads();
-    // ---- (c) quad layout: m[q][a] = M[a][j + 4 q] = C0 - Gram ------------------------------------------------------
+    // ---- (c) sweep layout: m[q][a] = M[a][j + LPR q] (staged as C0 - Gram) ------------------------------------------------------
     const bool valid = nb + rw < n_obs;
     const int64_t n = valid ? nb + rw : n_obs - 1;
     int nmiss = 0;
 #pragma unroll
-    for (int r = 0; r < SOLVE_ROWS; ++r) nmiss = (rw == r) ? cnt[r] : nmiss;
+    for (int r = 0; r < ROWS; ++r) nmiss = (rw == r) ? cnt[r] : nmiss;
     double m[CPL][MF];
     {
       const double* Mh = Mw + rw * MS_STRIDE;
 #pragma unroll
       for (int q = 0; q < CPL; ++q)
 #pragma unroll
-        for (int a = 0; a < MF; ++a) m[q][a] = C0s[a * MF + j + LPR * q] - Mh[a * 17 + j + LPR * q];
+        for (int a = 0; a < MF; ++a) m[q][a] = Mh[a * 17 + j + LPR * q];
     }
-    __syncwarp();
+    __syncwarp();   // the staging area is free again (reused for the output rows below)
     // every feature missing: unsupported by the reference (Util.hs:81); flagged, outputs zeroed below
     const bool empty = nmiss >= DD;
     if (empty && j == 0) set_err(p.scal, 2.0);
     // ---- (d) in-place inverse by symmetric sweeps: after sweeping k = 0..15 the matrix is -M_i^-1 ------------------
     // Step k (pivot p = M[k][k], d = 1/p):  B[i][l] = M[i][l] - M[i][k] M[k][l] d,  B[i][k] = M[i][k] d,  B[k][k] = -d.
-    // A lane reads M[k][c] from its own columns by symmetry; only column k travels (width-4 shuffles from its owner).
+    // A lane reads M[k][c] from its own columns by symmetry; only column k travels (width-LPR shuffles from its owner).
     // The owner keeps column k UNSCALED and remembers d in `scale` (applied once at the end), which keeps the update
     // formula identical in every lane (r = 0 makes it a no-op for the owner's column) -- no per-entry selects.
     bool ok = true;
@@ -220,7 +262,8 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_ker
       }
     }
     if (!LL) {
-      double* out = EA + n * EASF;
+      // rows [vech A | ez] of the warp's observations into the staging area, then out as ONE contiguous block
+      double* srow = Mw + rw * EAP;
 #pragma unroll
       for (int a = 0; a < MF; ++a) {
         const double ea = __shfl_sync(FULL, ez[a / LPR], a % LPR, LPR);
@@ -228,19 +271,26 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MINB) masked_solve_ker
         for (int q = 0; q < CPL; ++q) {
           const int c = j + LPR * q;
           const double v = empty ? 0.0 : fma(ea, ez[q], s2 * m[q][a]);
-          if (valid && a >= c) {
-            out[a * (a + 1) / 2 + c] = v;
-            mxa = max(mxa, (uint32_t)__double2hiint(v) & 0x7fffffffu);
+          if (a >= c) {
+            srow[a * (a + 1) / 2 + c] = v;
+            if (valid) mxa = max(mxa, (uint32_t)__double2hiint(v) & 0x7fffffffu);
           }
         }
       }
 #pragma unroll
-      for (int q = 0; q < CPL; ++q)
-        if (valid) {
-          const double v = empty ? 0.0 : ez[q];
-          out[NVF + j + LPR * q] = v;
-          mxe = max(mxe, (uint32_t)__double2hiint(v) & 0x7fffffffu);
-        }
+      for (int q = 0; q < CPL; ++q) {
+        const double v = empty ? 0.0 : ez[q];
+        srow[NVF + j + LPR * q] = v;
+        if (valid) mxe = max(mxe, (uint32_t)__double2hiint(v) & 0x7fffffffu);
+      }
+      __syncwarp();
+      const int nrows = (int)min((int64_t)ROWS, n_obs - nb);   // <= 0 for a warp past the end
+      if (nrows > 0) {
+        const double2* src = reinterpret_cast<const double2*>(Mw);
+        double2* dst = reinterpret_cast<double2*>(EA + nb * EASF);   // 1216-byte rows: 16-byte aligned
+        for (int e = lane; e < nrows * (EASF / 2); e += 32) dst[e] = src[(e / (EASF / 2)) * (EAP / 2) + e % (EASF / 2)];
+      }
+      __syncwarp();   // the next iteration's lists / matrices reuse the area
     } else {
       double dot = 0.0;
 #pragma unroll
@@ -401,31 +451,39 @@ int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart
   return GPLVM_OK;
 }
 
-template <int DD, bool LL>
+template <int DD, bool LL, int LPR>
 int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid) {
-  const int smem = ((DD + 1) * WP + MF * MF + SOLVE_WARPS * SOLVE_ROWS * MS_STRIDE) * (int)sizeof(double);
+  constexpr int smem = SolveCfg<LPR>::smem_bytes(DD);
   static bool attr_done[64] = {};
   if (!attr_done[sh.dev & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute((masked_solve_kernel<DD, LL>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute((masked_solve_kernel<DD, LL, LPR>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done[sh.dev & 63] = true;
   }
   if (!LL && sh.eamax) CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 24, sh.st));   // class maxima + precision-guard counters
-  GP_LAUNCH((masked_solve_kernel<DD, LL>), grid, SOLVE_WARPS * 32, smem, sh.st, bsrc, yy, sh.mbits, sh.n, sh.par, sh.EA, sh.partials,
+  GP_LAUNCH((masked_solve_kernel<DD, LL, LPR>), grid, SOLVE_WARPS * 32, smem, sh.st, bsrc, yy, sh.mbits, sh.n, sh.par, sh.EA, sh.partials,
             LL ? nullptr : sh.eamax);
   return GPLVM_OK;
+}
+
+// 4 lanes per observation (8 observations per warp, 1 CTA per SM): 12.6 ms at N = 2^23 against 13.6 ms for 8 lanes per
+// observation at 2 CTAs per SM (round-2 measurement, profiles/r2_masked_summary.md)
+template <int DD>
+int dispatch_solve(ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out) {
+  constexpr int LPR = 4;
+  int grid = (int)std::min<int64_t>(SolveCfg<LPR>::MINB * sm_count(sh.dev), ceil_div(sh.n, SOLVE_WARPS * SolveCfg<LPR>::ROWS));
+  if (grid > sh.nparts) grid = sh.nparts;
+  if (grid_out) *grid_out = grid;
+  return ll ? launch_solve<DD, true, LPR>(sh, bsrc, yy, grid) : launch_solve<DD, false, LPR>(sh, bsrc, yy, grid);
 }
 
 }  // namespace
 
 // E-step solve (ll = false) or likelihood terms (ll = true; per-CTA sums land in sh.partials[0 .. *grid_out))
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out) {
-  int grid = (int)std::min<int64_t>(SOLVE_MINB * sm_count(sh.dev), ceil_div(sh.n, SOLVE_WARPS * SOLVE_ROWS));
-  if (grid > sh.nparts) grid = sh.nparts;
-  if (grid_out) *grid_out = grid;
   switch (s->D) {
-    case 64: return ll ? launch_solve<64, true>(sh, bsrc, yy, grid) : launch_solve<64, false>(sh, bsrc, yy, grid);
-    case 128: return ll ? launch_solve<128, true>(sh, bsrc, yy, grid) : launch_solve<128, false>(sh, bsrc, yy, grid);
-    case 256: return ll ? launch_solve<256, true>(sh, bsrc, yy, grid) : launch_solve<256, false>(sh, bsrc, yy, grid);
+    case 64: return dispatch_solve<64>(sh, bsrc, yy, ll, grid_out);
+    case 128: return dispatch_solve<128>(sh, bsrc, yy, ll, grid_out);
+    case 256: return dispatch_solve<256>(sh, bsrc, yy, ll, grid_out);
     default: return fail(GPLVM_ERR_STATE, "fused masked solver: unsupported D");
   }
 }

@@ -137,6 +137,7 @@ int masked_restore(gplvm_ppca_session* s, double* restored, int64_t ld);
 // session.cu
 int session_allreduce_stats(gplvm_ppca_session* s, size_t count);
 int session_setup_p2p(gplvm_ppca_session* s);
+int session_peer_allreduce_stats(gplvm_ppca_session* s);   // dense.cu: in-place all-reduce of sh.stats over peer memory
 void session_release_p2p(gplvm_ppca_session* s);
 int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst = nullptr, double* scal = nullptr);  // scal: S_DONE skip flag block, default the session's
 

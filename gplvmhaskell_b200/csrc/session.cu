@@ -115,7 +115,9 @@ int session_setup_p2p(gplvm_ppca_session* s) {
   Context& c = ctx();
   s->p2p = false;
   const char* env = getenv("GPLVM_NO_P2P");
-  if (c.world < 2 || s->missing || !s->use_dmma || s->MP != 16 || s->D > 1024 || (env && atoi(env) != 0)) return GPLVM_OK;
+  const bool dense_ok = !s->missing && s->use_dmma && s->MP == 16 && s->D <= 1024;   // the fused dense step
+  const bool masked_ok = s->missing && s->S <= (1 << 20);                               // packed masked statistics (345 KB at D = 256)
+  if (c.world < 2 || !(dense_ok || masked_ok) || (env && atoi(env) != 0)) return GPLVM_OK;
   // [2 x S doubles | 2 x blocks uint64 flags | magic].  Rounded up to whole 2 MB granules: cudaIpcGetMemHandle names the
   // underlying ALLOCATION, and a small cudaMalloc may be sub-allocated at a non-zero offset inside one (the mapping a
   // peer opens would then point somewhere else).  Every mapping is additionally verified with a per-rank magic word.
@@ -329,7 +331,8 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
     if (e == cudaSuccess) e = cudaMemset(sh.parblock, 0, sizeof(double) * parlen);
     if (e == cudaSuccess) e = cudaMalloc(&sh.stats, sizeof(double) * (size_t)std::max<int64_t>(s->S, 3 * D));
     if (e == cudaSuccess) e = cudaMalloc(&sh.partials, sizeof(double) * (size_t)std::max<int64_t>(s->S, 3 * D) * sh.nparts);
-    if (e == cudaSuccess) e = cudaMalloc(&sh.scratch, sizeof(double) * (size_t)D * 8);
+    // per-feature scratch (8 D) + per-block W'^T W' partials of the masked update (ceil(D / 8) blocks x MP x MP)
+    if (e == cudaSuccess) e = cudaMalloc(&sh.scratch, sizeof(double) * ((size_t)D * 8 + (size_t)ceil_div(D, 8) * MP * MP));
     if (e == cudaSuccess) e = cudaEventCreate(&sh.ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&sh.ev1);
     if (e != cudaSuccess) {
