@@ -8,4 +8,6 @@ from .ppca import (PPCA, Left, Right, Session, make_ppca, make_ppca_type_safe, m
 from .gp import (ard_kernel, kernel_function, kernelFunction, gp_chol_lml, cholesky, tri_solve_lower,  # noqa: F401
                  gp_to_posterior_sample, gpToPosteriorSample)
 
-__version__ = "0.1.0"
+from .pca import PCA, make_pca, make_pca_type_safe, makePCA  # noqa: F401
+
+__version__ = "0.2.0"

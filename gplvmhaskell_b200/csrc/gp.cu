@@ -133,6 +133,7 @@ __device__ inline bool block_cholesky_128(double* Ls, double* dinv, int* flag) {
   const int LD = LDS_DIAG;
   if (tid == 0) *flag = 1;
   __syncthreads();
+#pragma unroll 1   // one copy of the (fully unrolled) 32-column step: the kernel stays within the instruction cache
   for (int c0 = 0; c0 < NB; c0 += 32) {
     if (warp == 0) {
       double m[32];

@@ -20,6 +20,7 @@ module GPLVM.B200
   , cholesky
   , triSolveLower
   , gpPosterior
+  , pca
   , setDevices
   ) where
 
@@ -55,6 +56,9 @@ foreign import ccall safe "gplvm_tri_solve_lower"
 foreign import ccall safe "gplvm_gp_posterior"
   c_gp_posterior :: Ptr Double -> Int64 -> Ptr Double -> Ptr Double -> Int64 -> Int64 -> Ptr Double -> Double
                  -> Double -> Double -> Ptr Double -> Int64 -> Ptr Double -> Ptr Double -> Ptr Double -> IO CInt
+foreign import ccall safe "gplvm_pca"
+  c_pca :: Ptr Double -> Int64 -> Int64 -> Int64 -> Ptr Double -> Ptr Double -> Ptr Double -> Ptr Double
+        -> Ptr Double -> Ptr Double -> Ptr CInt -> IO CInt
 foreign import ccall safe "gplvm_set_devices"
   c_set_devices :: CInt -> IO CInt
 foreign import ccall unsafe "gplvm_last_error"
@@ -203,6 +207,27 @@ gpPosterior observe train yTrain invL2 variance jitterTrain jitterPost normals =
       check rc
       pure (Just (fromForeignPtr (Z :. nObs) meanOut, fromForeignPtr (Z :. nObs :. nObs) postOut,
                   fromForeignPtr (Z :. nObs :. nSamples) sampOut))
+
+-- | makePCA (src/GPLVM/PCA.hs:35-62) for an N x D input with the observations as ROWS, keeping d eigenvectors:
+-- (mean (D), covariance (D x D), eigenvalues (D, descending), eigenvectors (D x d, columns), finalData (N x d),
+-- restoredData (N x D)).  meanCovS / eigSH / mulP / pinvS of the reference all run inside the one call.
+pca :: Array F DIM2 Double -> Int
+    -> (Array F DIM1 Double, Array F DIM2 Double, Array F DIM1 Double, Array F DIM2 Double, Array F DIM2 Double, Array F DIM2 Double)
+pca x dKeep = unsafePerformIO $ do
+  let Z :. n :. dFeat = extent x
+      d = min dKeep dFeat
+  meanOut <- mallocForeignPtrArray dFeat
+  covOut <- mallocForeignPtrArray (dFeat * dFeat)
+  valsOut <- mallocForeignPtrArray dFeat
+  vecsOut <- mallocForeignPtrArray (dFeat * d)
+  finalOut <- mallocForeignPtrArray (n * d)
+  restOut <- mallocForeignPtrArray (n * dFeat)
+  withForeignPtr (toForeignPtr x) $ \px -> withForeignPtr meanOut $ \pm -> withForeignPtr covOut $ \pc ->
+    withForeignPtr valsOut $ \pv -> withForeignPtr vecsOut $ \pe -> withForeignPtr finalOut $ \pf ->
+      withForeignPtr restOut $ \pr -> alloca $ \psw ->
+        check =<< c_pca px (fromIntegral n) (fromIntegral dFeat) (fromIntegral dKeep) pm pc pv pe pf pr psw
+  pure ( fromForeignPtr (Z :. dFeat) meanOut, fromForeignPtr (Z :. dFeat :. dFeat) covOut, fromForeignPtr (Z :. dFeat) valsOut
+       , fromForeignPtr (Z :. dFeat :. d) vecsOut, fromForeignPtr (Z :. n :. d) finalOut, fromForeignPtr (Z :. n :. dFeat) restOut )
 
 -- | Number of GPUs of this process the library shards observations over (include/gplvm_b200.h: gplvm_set_devices).
 setDevices :: Int -> IO ()

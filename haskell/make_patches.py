@@ -134,6 +134,27 @@ def patch_gp_example(lines):
     return lines
 
 
+def patch_pca(lines):
+    lines = insert_after(lines, "import GPLVM.Types", ["import qualified GPLVM.B200 as B200"])
+    a = find(lines, "makePCA desiredDimensions input =")
+    b = find(lines, "  in PCA{..}", a)
+    body = [
+        "makePCA desiredDimensions input =",
+        "  -- meanCovS, eigSH, the projection and the pseudo-inverse restore run in libgplvm_b200 (gplvm_pca)",
+        "  let _inputData = input",
+        "      (Z :. yInp :. _) = extent input",
+        "      (meanVec, cov, evals, evecs, final, restored) = B200.pca (computeS input) desiredDimensions",
+        "      _meanMatrix = extend (Z :. yInp :. All) (delay meanVec)",
+        "      _covariance = trustSym cov",
+        "      _eigenValues = evals",
+        "      _eigenVectors = delay evecs     -- columns are eigenvectors",
+        "      _finalData = delay final        -- data in the eigenvector basis",
+        "      _restoredData = delay restored  -- back in the original space, mean added",
+        "  in PCA{..}",
+    ]
+    return lines[:a] + body + lines[b + 1:]
+
+
 def patch_cabal(lines):
     i = find(lines, "      GPLVM.GPExample")
     lines = lines[:i] + ["      GPLVM.B200"] + lines[i:]
@@ -146,6 +167,7 @@ def patch_cabal(lines):
 TARGETS = [
     ("PPCA.patch", "src/GPLVM/PPCA.hs", patch_ppca),
     ("TypeSafe-PPCA.patch", "src/GPLVM/TypeSafe/PPCA.hs", patch_typesafe_ppca),
+    ("PCA.patch", "src/GPLVM/PCA.hs", patch_pca),
     ("GaussianProcess.patch", "src/GPLVM/GaussianProcess.hs", patch_gaussian_process),
     ("GPExample.patch", "src/GPLVM/GPExample.hs", patch_gp_example),
     ("cabal.patch", "GPLVMHaskell.cabal", patch_cabal),

@@ -115,6 +115,20 @@ int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train
                        const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out,
                        double* samples_out);
 
+/* makePCA, src/GPLVM/PCA.hs:35-62 (typed twin src/GPLVM/TypeSafe/PCA.hs:56-92): PCA by eigendecomposition.
+ * NOTE the layout: X is N x D row-major with the OBSERVATIONS AS ROWS -- the reference's PCA works on rows (hmatrix
+ * meanCovS, PCA.hs:42), unlike its PPCA (D x N).
+ *   mean_out (D)            = meanVec of meanCovS (one row of _meanMatrix, PCA.hs:43)
+ *   cov_out (D x D)         = _covariance = Xc^T Xc / (N - 1)
+ *   eigvals_out (D)         = _eigenValues, descending (eigSH, PCA.hs:45)
+ *   eigvecs_out (D x d)     = _eigenVectors: the first d = min(d_keep, D) eigenvectors as COLUMNS (PCA.hs:48-53); sign
+ *                             convention: the entry of largest magnitude of every eigenvector is positive
+ *   final_out (N x d)       = _finalData = Xc . eigvecs (PCA.hs:55-56)
+ *   restored_out (N x D)    = _restoredData = final . eigvecs^T + mean (PCA.hs:58-60; pinvS of orthonormal rows)
+ * Every output pointer may be NULL; sweeps_out (nullable) receives the number of Jacobi sweeps.  Single GPU. */
+int gplvm_pca(const double* X, int64_t N, int64_t D, int64_t d_keep, double* mean_out, double* cov_out, double* eigvals_out,
+              double* eigvecs_out, double* final_out, double* restored_out, int* sweeps_out);
+
 /* ---- session API: observation shards resident in HBM ---------------------------------------
  * Used by the one-shot calls above, by bench.py (inputs already resident when the timed region
  * starts) and by multi-process launches (one process per GPU).  A session holds this process's

@@ -80,7 +80,7 @@ def test_export_list_is_defined_and_every_import_is_used():
     text, imports = hs_imports()
     exports = re.search(r"module GPLVM\.B200\s*\((.*?)\)\s*where", text, flags=re.S).group(1)
     names = [n.strip() for n in exports.split(",") if n.strip()]
-    assert {"ppcaDense", "ppcaMissing", "ppca", "rbfKernel", "gpCholLml", "cholesky", "triSolveLower", "gpPosterior"} <= set(names)
+    assert {"ppcaDense", "ppcaMissing", "ppca", "rbfKernel", "gpCholLml", "cholesky", "triSolveLower", "gpPosterior", "pca"} <= set(names)
     for n in names:
         assert re.search(r"^%s\s*::" % re.escape(n), text, flags=re.M), "%s has no type signature" % n
         assert re.search(r"^%s\b[^:\n]*=" % re.escape(n), text, flags=re.M), "%s is exported but not defined" % n
@@ -115,6 +115,8 @@ def test_patches_are_current_and_apply(tmp_path):
     gp = (work / "src/GPLVM/GaussianProcess.hs").read_text()
     assert gp.count("cholGP $") == 2 and gp.count("solveGP cholK") == 2 and "B200.triSolveLower" in gp
     assert "GPLVM.B200" in (work / "GPLVMHaskell.cabal").read_text()
+    pca = (work / "src/GPLVM/PCA.hs").read_text()
+    assert "B200.pca (computeS input) desiredDimensions" in pca and "eigSH" not in pca and "meanCovS" not in pca
     # the emptied bodies: no hmatrix call is left on the EM path of either variant
     for src in (ppca, typed):
         body = src[src.index("emStepsFast"):]
