@@ -116,7 +116,7 @@ def test_patches_are_current_and_apply(tmp_path):
     assert gp.count("cholGP $") == 2 and gp.count("solveGP cholK") == 2 and "B200.triSolveLower" in gp
     assert "GPLVM.B200" in (work / "GPLVMHaskell.cabal").read_text()
     pca = (work / "src/GPLVM/PCA.hs").read_text()
-    assert "B200.pca (computeS input) desiredDimensions" in pca and "eigSH" not in pca and "meanCovS" not in pca
+    assert "B200.pca (computeS input) desiredDimensions" in pca and "= eigSH" not in pca and "= meanCovS" not in pca
     # the emptied bodies: no hmatrix call is left on the EM path of either variant
     for src in (ppca, typed):
         body = src[src.index("emStepsFast"):]
