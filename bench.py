@@ -491,23 +491,31 @@ def run_ppca(env: Env, args, n_obs: int, missing: bool, steps: int, warmup: int,
         else:
             env.barrier()
             t0 = time.perf_counter()
+            ph = {}
             s2 = g.Session(D, n_obs, M, missing=missing, obs_begin=begin, obs_count=count)
+            ph["create"] = time.perf_counter() - t0
             s2.load_host(Yh)
+            ph["load_host"] = time.perf_counter() - t0
             s2.init(W0, 1.0)
+            ph["init"] = time.perf_counter() - t0
             s2.steps(steps)
             pp = s2.params()
+            ph["steps+params"] = time.perf_counter() - t0
             llv = s2.loglik()
+            ph["loglik"] = time.perf_counter() - t0
             d2h = 8 * (D * M + 2)
             if missing:
                 _lib.check(lib.gplvm_session_restored(s2.h, _lib.dptr(Yh), count))
                 d2h += 8 * D * count
+                ph["restored"] = time.perf_counter() - t0
             env.barrier()
             dt = time.perf_counter() - t0
             s2.close()
+            e2e_phases = {k: round(v, 4) for k, v in ph.items()}   # cumulative seconds on rank 0
             what = ("one process per GPU, each rank drives the C-ABI session API on its pinned host shard: create + load_host "
                     "(H2D, reference layout) + init + %d EM steps + params + log-likelihood%s; NOT a single one-shot call"
                     % (steps, " + restored matrix D2H" if missing else ""))
-            e2e_parity = {"sigma2": pp["sigma2"], "loglik": llv, "em_steps": int(pp["steps"])}
+            e2e_parity = {"sigma2": pp["sigma2"], "loglik": llv, "em_steps": int(pp["steps"]), "cumulative_s_rank0": e2e_phases}
         dt = env.max_over_ranks(dt)
         e2e = {"value": steps / dt, "unit": "iterations/s", "h2d_bytes_per_step": 8 * D * n_obs / steps,
                "d2h_bytes_per_step": d2h * (env.world if missing else 1) / steps, "seconds": dt, "what": what, "result": e2e_parity}

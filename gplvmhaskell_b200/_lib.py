@@ -48,6 +48,8 @@ SIGNATURES = {
     "gplvm_tri_solve_lower": (C.c_int, [_c_double_p, C.c_int64, _c_double_p, C.c_int64, _c_double_p]),
     "gplvm_gp_posterior": (C.c_int, [_c_double_p, C.c_int64, _c_double_p, _c_double_p, C.c_int64, C.c_int64, _c_double_p, C.c_double,
                                      C.c_double, C.c_double, _c_double_p, C.c_int64, _c_double_p, _c_double_p, _c_double_p]),
+    "gplvm_gp_posterior_upper": (C.c_int, [_c_double_p, C.c_int64, _c_double_p, _c_double_p, C.c_int64, C.c_int64, _c_double_p, C.c_double,
+                                           C.c_double, C.c_double, _c_double_p, C.c_int64, _c_double_p, _c_double_p, _c_double_p]),
     "gplvm_pca": (C.c_int, [_c_double_p, C.c_int64, C.c_int64, C.c_int64, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                             _c_double_p, _c_double_p, _c_int_p]),
     "gplvm_dist_unique_id": (C.c_int, [C.c_void_p]),

@@ -554,6 +554,43 @@ int tri_solve_device(const double* dL, int64_t N, int64_t ld, double* dB, int64_
   return GPLVM_OK;
 }
 
+// X (N x R) = L^-T B (back substitution with the UPPER factor U = L^T: the solve hmatrix performs when cholSH hands
+// linearSolveS the upper factor, see gplvm_gp_posterior_upper), blocked bottom-up.  Same simple CUDA-core kernels.
+__global__ void __launch_bounds__(256) tri_diag_apply_t_kernel(const double* __restrict__ Tinv, int nb, const double* __restrict__ B,
+                                                               double* __restrict__ Xo, int64_t R, int64_t k0) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  for (int i = 0; i < nb; ++i) {   // (L_kk^-T)[i][k] = Tinv[k][i], k >= i
+    double s = 0.0;
+    for (int k = i; k < nb; ++k) s = fma(Tinv[k * NB + i], B[(k0 + k) * R + r], s);
+    Xo[(k0 + i) * R + r] = s;
+  }
+}
+__global__ void __launch_bounds__(256) tri_update_t_kernel(const double* __restrict__ L, int64_t ld, int64_t k0, int nb,
+                                                           const double* __restrict__ Xo, double* __restrict__ B, int64_t R, int64_t i0) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = i0 + blockIdx.y;   // a row above the block: B[i] -= sum_k L[k0 + k][i] X[k0 + k]
+  if (r >= R || i >= k0) return;
+  double s = 0.0;
+  for (int k = 0; k < nb; ++k) s = fma(L[(k0 + k) * ld + i], Xo[(k0 + k) * R + r], s);
+  B[i * R + r] -= s;
+}
+int tri_solve_t_device(const double* dL, int64_t N, int64_t ld, double* dB, int64_t R, double* dX, double* dT, double* dstate,
+                       cudaStream_t st) {
+  const int64_t nblocks = ceil_div(N, NB);
+  for (int64_t b = nblocks - 1; b >= 0; --b) {
+    const int64_t k0 = b * NB;
+    const int nb = (int)std::min<int64_t>(NB, N - k0);
+    GP_LAUNCH(tri_inverse_kernel, 1, 256, DIAG_SMEM, st, dL, ld, k0, nb, dT, dstate);
+    GP_LAUNCH(tri_diag_apply_t_kernel, (unsigned)ceil_div(R, 256), 256, 0, st, dT, nb, dB, dX, R, k0);
+    for (int64_t i0 = 0; i0 < k0; i0 += 32768) {
+      dim3 grid((unsigned)ceil_div(R, 256), (unsigned)std::min<int64_t>(32768, k0 - i0));
+      GP_LAUNCH(tri_update_t_kernel, grid, 256, 0, st, dL, ld, k0, nb, dX, dB, R, i0);
+    }
+  }
+  return GPLVM_OK;
+}
+
 // posterior pieces of gpToPosteriorSample (GaussianProcess.hs:80-98)
 // mean[i] = sum_k alpha[k] Lk[k][i]                                                     (:80)
 __global__ void __launch_bounds__(256) gp_post_mean_kernel(const double* __restrict__ alpha, const double* __restrict__ Lk, int64_t nt,
@@ -585,6 +622,24 @@ __global__ void __launch_bounds__(256) gp_post_sample_kernel(const double* __res
   double acc = mean[i];
   for (int64_t k = 0; k <= i; ++k) acc = fma(P[i * ldc + k], normals[k * S + sidx], acc);
   out[i * S + sidx] = acc;
+}
+
+// samples (no x S) = mean 1^T + U normals with U = P^T upper (P lower, no x ldc)
+__global__ void __launch_bounds__(256) gp_post_sample_upper_kernel(const double* __restrict__ P, int64_t ldc, int64_t no,
+                                                                   const double* __restrict__ mean, const double* __restrict__ normals,
+                                                                   int64_t S, double* __restrict__ out) {
+  const int64_t i = blockIdx.y;
+  const int64_t sidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= S) return;
+  double acc = mean[i];
+  for (int64_t k = i; k < no; ++k) acc = fma(P[k * ldc + i], normals[k * S + sidx], acc);
+  out[i * S + sidx] = acc;
+}
+// U (N x N dense, row-major) = L^T with the strict lower part zero
+__global__ void gp_transpose_factor_kernel(const double* __restrict__ L, int64_t ld, int64_t N, double* __restrict__ U) {
+  const int64_t i = blockIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N) U[i * N + j] = (j >= i) ? L[j * ld + i] : 0.0;
 }
 
 struct DevBuf {
@@ -624,9 +679,18 @@ int factorise(double* dA, int64_t N, int64_t ld, const KernelSpec* gen, double* 
     const int nb0 = (int)std::min<int64_t>(NB, N);
     GP_LAUNCH(gp_first_panel_kernel, (unsigned)N, 128, 0, st, dA, ld, nb0, ks);
   }
-  // Two-level blocking: outer panels of 2 NB = 256 columns.  Inside an outer panel two NB-wide inner panels are
-  // factorised (diag + panel GEMM) with one block-column update between them; the trailing matrix is then updated
-  // ONCE with K = 256, which halves the read-modify-write traffic of the big update and its epilogue overhead.
+  // Two-level blocking: outer panels of NI NB columns (NI = 8: 1024; N = 32768: 435 / 422 / 414 ms at NI = 2 / 4 / 8).  Inside an outer panel the NI inner panels are
+  // factorised one after the other (block-column update with the inner panels before it, diag, panel GEMM); the trailing
+  // matrix is then updated ONCE with K = NI NB, which divides the read-modify-write traffic of the big update and its
+  // prologue / epilogue overhead per flop by NI (measured on the trailing update: 77 % of the DMMA peak at K = 256).
+  // The panel chain of an outer step (NI diagonal blocks at 280 us each, NI panel GEMMs, block-column and head updates)
+  // runs on the look-ahead stream and must hide under the tail update: 6.7 ms per step at NI = 8, which a K = 1024 tail
+  // covers only while more than ~14 000 columns remain.  NI therefore shrinks with the remaining matrix: 8 / 4 / 2.
+  static const int NI_FIXED = []() {
+    const char* e = getenv("GPLVM_GP_INNER");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 1 && v <= 32) ? v : 0;
+  }();
   auto panel = [&](cudaStream_t sx, int64_t k0, int nb) -> int {   // L21 = A21 T^T for the rows below the diagonal block at k0
     const int64_t r0 = k0 + nb;
     const int64_t T = ceil_div(N - r0, NB);
@@ -645,8 +709,8 @@ int factorise(double* dA, int64_t N, int64_t ld, const KernelSpec* gen, double* 
                 nullptr, nullptr, ks, column_only ? 1 : 0);
     return GPLVM_OK;
   };
-  // Look-ahead over two streams.  `sp` (high priority) runs the latency-bound panel work of outer step k + 1 (two
-  // diagonal blocks, two panel GEMMs, one block-column update) and the "head" of update k (the next 256 columns);
+  // Look-ahead over two streams.  `sp` (high priority) runs the latency-bound panel work of outer step k + 1 (NI
+  // diagonal blocks, NI panel GEMMs, NI - 1 block-column updates) and the "head" of update k (the next NI block columns);
   // `st` runs the "tail" of update k (everything right of the head) -- the bulk of the flops -- back to back.
   //   head(k) needs tail(k-1) (same region) and panel(k);  tail(k) needs panel(k) and tail(k-1);
   //   panel(k+1) needs head(k) only, so it hides under tail(k).
@@ -656,28 +720,34 @@ int factorise(double* dA, int64_t N, int64_t ld, const KernelSpec* gen, double* 
   CUDA_TRY(cudaEventRecord(ev_start, st));
   CUDA_TRY(cudaStreamWaitEvent(sp, ev_start, 0));
   bool tail_pending = false;
-  for (int64_t K0 = 0; K0 < N; K0 += 2 * NB) {
+  int NI = 2;
+  for (int64_t K0 = 0; K0 < N; K0 += (int64_t)NI * NB) {
+    const int64_t left = N - K0;
+    static const int64_t T8 = getenv("GPLVM_GP_T8") ? atoll(getenv("GPLVM_GP_T8")) : 16384;
+    static const int64_t T4 = getenv("GPLVM_GP_T4") ? atoll(getenv("GPLVM_GP_T4")) : 8192;
+    static const int64_t T2 = getenv("GPLVM_GP_T2") ? atoll(getenv("GPLVM_GP_T2")) : 0;
+    NI = NI_FIXED ? NI_FIXED : (left > T8 ? 8 : (left > T4 ? 4 : (left > T2 ? 2 : 1)));
     const bool generate = gen && K0 == 0;
-    const int nb1 = (int)std::min<int64_t>(NB, N - K0);
-    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, sp, dA, ld, K0, nb1, dTinv, dy, dalpha, dstate);
-    const int64_t r1 = K0 + nb1;
-    if (r1 >= N) break;
-    GP_TRY(panel(sp, K0, nb1));
-    GP_TRY(update(sp, K0, nb1, r1, true, generate));     // block column [r1, r1 + NB) only (K = 128)
-    const int nb2 = (int)std::min<int64_t>(NB, N - r1);
-    GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, sp, dA, ld, r1, nb2, dTinv, dy, dalpha, dstate);
-    const int64_t r2 = r1 + nb2;
-    if (r2 >= N) break;
-    GP_TRY(panel(sp, r1, nb2));
+    int64_t c0 = K0;
+    bool done = false;
+    for (int ip = 0; ip < NI; ++ip) {
+      const int nb = (int)std::min<int64_t>(NB, N - c0);
+      if (ip > 0) GP_TRY(update(sp, K0, (int)(c0 - K0), c0, true, generate));   // block column [c0, c0 + NB), K = ip NB
+      GP_LAUNCH(gp_diag_kernel, 1, 256, diag_smem, sp, dA, ld, c0, nb, dTinv, dy, dalpha, dstate);
+      c0 += nb;
+      if (c0 >= N) { done = true; break; }
+      GP_TRY(panel(sp, c0 - nb, nb));
+    }
+    if (done) break;
+    const int Kdim = (int)(c0 - K0);   // = NI NB
     CUDA_TRY(cudaEventRecord(ev_panel, sp));
-    // head: the two block columns [r2, r2 + 128) and [r2 + 128, r2 + 256), K = 256
+    // head: the NI block columns the next outer step factorises
     if (tail_pending) CUDA_TRY(cudaStreamWaitEvent(sp, ev_tail, 0));
-    GP_TRY(update(sp, K0, nb1 + nb2, r2, true, generate));
-    if (r2 + NB < N) GP_TRY(update(sp, K0, nb1 + nb2, r2 + NB, true, generate));
+    for (int ib = 0; ib < NI && c0 + (int64_t)ib * NB < N; ++ib) GP_TRY(update(sp, K0, Kdim, c0 + (int64_t)ib * NB, true, generate));
     // tail: the trailing matrix right of the head
-    if (r2 + 2 * NB < N) {
+    if (c0 + (int64_t)NI * NB < N) {
       CUDA_TRY(cudaStreamWaitEvent(st, ev_panel, 0));
-      GP_TRY(update(st, K0, nb1 + nb2, r2 + 2 * NB, false, generate));
+      GP_TRY(update(st, K0, Kdim, c0 + (int64_t)NI * NB, false, generate));
       CUDA_TRY(cudaEventRecord(ev_tail, st));
       tail_pending = true;
     }
@@ -834,9 +904,15 @@ int gplvm_tri_solve_lower(const double* L, int64_t N, const double* B, int64_t R
 }
 
 
-int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train, const double* y_train, int64_t n_train, int64_t Q,
-                       const double* inv_lengthscale2, double variance, double jitter_train, double jitter_post,
-                       const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out, double* samples_out) {
+}  // extern "C"
+
+// upper = false: both Cholesky factors lower (K = L L^T), forward substitutions -- the textbook GP posterior.
+// upper = true : the reference read literally with hmatrix's UPPER factor U = L^T (K = U^T U): linearSolveS cholK b solves
+//                U x = b (GaussianProcess.hs:74,77), the mean is (U^-1 y)^T (U^-1 K_s) (:80), the posterior factor is the upper
+//                factor of K_ss + jitter I - Z^T Z (:83-86) and the samples are mean + U_post normals (:89).
+static int gp_posterior_impl(bool upper, const double* X_obs, int64_t n_obs, const double* X_train, const double* y_train, int64_t n_train,
+                             int64_t Q, const double* inv_lengthscale2, double variance, double jitter_train, double jitter_post,
+                             const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out, double* samples_out) {
   if (!X_obs || !X_train || !y_train || !inv_lengthscale2 || !mean_out) return fail(GPLVM_ERR_ARG, "gplvm_gp_posterior: null argument");
   if (n_obs < 1 || n_train < 1 || Q < 1 || Q > 64) return fail(GPLVM_ERR_ARG, "gplvm_gp_posterior: sizes must be positive (Q <= 64)");
   if (samples_out && (!normals || n_samples < 1)) return fail(GPLVM_ERR_ARG, "gplvm_gp_posterior: normals required for samples");
@@ -848,7 +924,7 @@ int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train
   cudaStream_t st = c.shards[0].stream;
   GP_TRY(set_gemm_attrs());
   const int64_t ldk = padded_ld(n_train), ldc = padded_ld(n_obs), ldt = round_up(n_train, 4);
-  DevBuf dXo, dXt, dl, dK, dy, dal, dT, dst, dKs, dLk, dLkT, dC, dmean, dnorm, dsamp;
+  DevBuf dXo, dXt, dl, dK, dy, dal, dT, dst, dKs, dLk, dLkT, dC, dmean, dnorm, dsamp, dU;
   CUDA_TRY(cudaMalloc(&dXo.p, sizeof(double) * n_obs * Q));
   CUDA_TRY(cudaMalloc(&dXt.p, sizeof(double) * n_train * Q));
   CUDA_TRY(cudaMalloc(&dl.p, sizeof(double) * Q));
@@ -869,7 +945,13 @@ int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train
   CUDA_TRY(cudaMemcpyAsync(dy.p, y_train, sizeof(double) * n_train, cudaMemcpyHostToDevice, st));
   // L = chol(K(train, train) + jitter I), alpha = L^-1 y                                   (GaussianProcess.hs:64-68,77)
   KernelSpec kt{dXt.as<double>(), dl.as<double>(), variance, jitter_train, (int)Q};
-  GP_TRY(factorise(dK.as<double>(), n_train, ldk, &kt, dy.as<double>(), dal.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  if (!upper) {
+    GP_TRY(factorise(dK.as<double>(), n_train, ldk, &kt, dy.as<double>(), dal.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  } else {
+    GP_TRY(factorise(dK.as<double>(), n_train, ldk, &kt, nullptr, nullptr, dT.as<double>(), dst.as<double>(), st));
+    // a = U^-1 y = L^-T y                                                                  (GaussianProcess.hs:77, upper reading)
+    GP_TRY(tri_solve_t_device(dK.as<double>(), n_train, ldk, dy.as<double>(), 1, dal.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  }
   // K_s = k(observe, train): n_train x n_obs (orientation of sqDist, GPExample.hs:83)     (GaussianProcess.hs:71)
   for (int64_t jj = 0; jj < n_train; jj += 32768) {
     const int64_t jn = std::min<int64_t>(32768, n_train - jj);
@@ -878,7 +960,10 @@ int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train
               dKs.as<double>() + jj * n_obs, n_obs, jj, jn);
   }
   // Lk = L^-1 K_s                                                                         (GaussianProcess.hs:74)
-  GP_TRY(tri_solve_device(dK.as<double>(), n_train, ldk, dKs.as<double>(), n_obs, dLk.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  if (!upper)
+    GP_TRY(tri_solve_device(dK.as<double>(), n_train, ldk, dKs.as<double>(), n_obs, dLk.as<double>(), dT.as<double>(), dst.as<double>(), st));
+  else   // Z = U^-1 K_s = L^-T K_s
+    GP_TRY(tri_solve_t_device(dK.as<double>(), n_train, ldk, dKs.as<double>(), n_obs, dLk.as<double>(), dT.as<double>(), dst.as<double>(), st));
   GP_LAUNCH(gp_post_mean_kernel, (unsigned)ceil_div(n_obs, 256), 256, 0, st, dal.as<double>(), dLk.as<double>(), n_train, n_obs,
             dmean.as<double>());
   CUDA_TRY(cudaMemcpyAsync(mean_out, dmean.p, sizeof(double) * n_obs, cudaMemcpyDeviceToHost, st));
@@ -896,14 +981,24 @@ int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train
                 dLkT.as<double>(), ldt, (int64_t)0, n_obs, (int64_t)0, (int)ldt, nullptr, nullptr, ko, 0);
     }
     GP_TRY(factorise(dC.as<double>(), n_obs, ldc, nullptr, nullptr, nullptr, dT.as<double>(), dst.as<double>() + 4, st));
-    if (postfactor_out) GP_TRY(copy_lower_to_host(dC.as<double>(), n_obs, ldc, postfactor_out, st));
+    if (postfactor_out && !upper) GP_TRY(copy_lower_to_host(dC.as<double>(), n_obs, ldc, postfactor_out, st));
+    if (postfactor_out && upper) {
+      CUDA_TRY(cudaMalloc(&dU.p, sizeof(double) * (size_t)n_obs * n_obs));
+      dim3 grid((unsigned)ceil_div(n_obs, 256), (unsigned)n_obs);
+      GP_LAUNCH(gp_transpose_factor_kernel, grid, 256, 0, st, dC.as<double>(), ldc, n_obs, dU.as<double>());
+      CUDA_TRY(cudaMemcpyAsync(postfactor_out, dU.p, sizeof(double) * (size_t)n_obs * n_obs, cudaMemcpyDeviceToHost, st));
+    }
     if (samples_out) {
       CUDA_TRY(cudaMalloc(&dnorm.p, sizeof(double) * (size_t)n_obs * n_samples));
       CUDA_TRY(cudaMalloc(&dsamp.p, sizeof(double) * (size_t)n_obs * n_samples));
       CUDA_TRY(cudaMemcpyAsync(dnorm.p, normals, sizeof(double) * (size_t)n_obs * n_samples, cudaMemcpyHostToDevice, st));
       dim3 grid((unsigned)ceil_div(n_samples, 256), (unsigned)n_obs);
-      GP_LAUNCH(gp_post_sample_kernel, grid, 256, 0, st, dC.as<double>(), ldc, n_obs, dmean.as<double>(), dnorm.as<double>(), n_samples,
-                dsamp.as<double>());
+      if (!upper)
+        GP_LAUNCH(gp_post_sample_kernel, grid, 256, 0, st, dC.as<double>(), ldc, n_obs, dmean.as<double>(), dnorm.as<double>(), n_samples,
+                  dsamp.as<double>());
+      else
+        GP_LAUNCH(gp_post_sample_upper_kernel, grid, 256, 0, st, dC.as<double>(), ldc, n_obs, dmean.as<double>(), dnorm.as<double>(),
+                  n_samples, dsamp.as<double>());
       CUDA_TRY(cudaMemcpyAsync(samples_out, dsamp.p, sizeof(double) * (size_t)n_obs * n_samples, cudaMemcpyDeviceToHost, st));
     }
   }
@@ -914,6 +1009,22 @@ int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train
   if (state[1] != 0.0 || state[5] != 0.0)
     return fail(GPLVM_ERR_NUMERIC, "gplvm_gp_posterior: matrix not positive definite (the reference's cholSH throws; Maybe result Nothing)");
   return GPLVM_OK;
+}
+
+extern "C" {
+
+int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train, const double* y_train, int64_t n_train, int64_t Q,
+                       const double* inv_lengthscale2, double variance, double jitter_train, double jitter_post,
+                       const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out, double* samples_out) {
+  return gp_posterior_impl(false, X_obs, n_obs, X_train, y_train, n_train, Q, inv_lengthscale2, variance, jitter_train, jitter_post, normals,
+                           n_samples, mean_out, postfactor_out, samples_out);
+}
+
+int gplvm_gp_posterior_upper(const double* X_obs, int64_t n_obs, const double* X_train, const double* y_train, int64_t n_train, int64_t Q,
+                             const double* inv_lengthscale2, double variance, double jitter_train, double jitter_post,
+                             const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out, double* samples_out) {
+  return gp_posterior_impl(true, X_obs, n_obs, X_train, y_train, n_train, Q, inv_lengthscale2, variance, jitter_train, jitter_post, normals,
+                           n_samples, mean_out, postfactor_out, samples_out);
 }
 
 }  // extern "C"

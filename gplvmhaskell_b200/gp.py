@@ -85,10 +85,13 @@ def tri_solve_lower(L, B) -> np.ndarray:
 
 
 def gp_to_posterior_sample(observe, x_train, y_train, normals=None, inv_lengthscale2=(1.0 / 0.1,), variance: float = 1.0,
-                           jitter_train: float = 0.00005, jitter_post: float = 1.0e-6):
+                           jitter_train: float = 0.00005, jitter_post: float = 1.0e-6, factor: str = "lower"):
     """gpToPosteriorSample (GaussianProcess.hs:51-98) with caller-supplied standard normals (n_obs x n_samples; the
     reference draws them from mkStdGen (-4)).  Returns (mean, posterior_factor, samples or None); raises GplvmError
-    where the reference returns Nothing / cholSH throws."""
+    where the reference returns Nothing / cholSH throws.  ``factor="upper"`` reads the reference literally with hmatrix's
+    upper Cholesky factor (gplvm_gp_posterior_upper; see include/gplvm_b200.h): different mean / factor / samples."""
+    if factor not in ("lower", "upper"):
+        raise ValueError("factor must be 'lower' or 'upper'")
     lib = _lib.load()
     Xo = np.ascontiguousarray(np.asarray(observe, dtype=np.float64).reshape(len(observe), -1))
     Xt = np.ascontiguousarray(np.asarray(x_train, dtype=np.float64).reshape(len(x_train), -1))
@@ -108,7 +111,8 @@ def gp_to_posterior_sample(observe, x_train, y_train, normals=None, inv_lengthsc
         nrm = np.ascontiguousarray(np.asarray(normals, dtype=np.float64).reshape(no, -1))
         ns = nrm.shape[1]
         samples = np.empty((no, ns))
-    _lib.check(lib.gplvm_gp_posterior(_lib.dptr(Xo), no, _lib.dptr(Xt), _lib.dptr(yt), nt, q, _lib.dptr(il2), float(variance),
+    fn = lib.gplvm_gp_posterior if factor == "lower" else lib.gplvm_gp_posterior_upper
+    _lib.check(fn(_lib.dptr(Xo), no, _lib.dptr(Xt), _lib.dptr(yt), nt, q, _lib.dptr(il2), float(variance),
                                       float(jitter_train), float(jitter_post), _lib.dptr(nrm), ns, _lib.dptr(mean), _lib.dptr(post),
                                       _lib.dptr(samples)))
     return mean, post, samples

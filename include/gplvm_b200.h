@@ -115,6 +115,17 @@ int gplvm_gp_posterior(const double* X_obs, int64_t n_obs, const double* X_train
                        const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out,
                        double* samples_out);
 
+/* The same pipeline read LITERALLY with hmatrix's factor convention: `chol` / cholSH return the UPPER factor U (K = U^T U)
+ * and the reference hands it to linearSolveS as is (GaussianProcess.hs:67-77), so it solves U x = b:
+ *   Z = U^-1 K_s,  a = U^-1 y,  mean = a^T Z = y^T (U U^T)^-1 K_s   (not the textbook y^T K^-1 K_s),
+ *   postfactor_out = U_post (upper, K_ss + jitter_post I - Z^T Z = U_post^T U_post),  samples = mean 1^T + U_post normals.
+ * Whether the repa-linear-algebra fork's cholSH returns U or L cannot be determined offline; callers that
+ * need bit-for-bit agreement with a GHC build of the reference pick the variant that matches it. */
+int gplvm_gp_posterior_upper(const double* X_obs, int64_t n_obs, const double* X_train, const double* y_train, int64_t n_train,
+                             int64_t Q, const double* inv_lengthscale2, double variance, double jitter_train, double jitter_post,
+                             const double* normals, int64_t n_samples, double* mean_out, double* postfactor_out,
+                             double* samples_out);
+
 /* makePCA, src/GPLVM/PCA.hs:35-62 (typed twin src/GPLVM/TypeSafe/PCA.hs:56-92): PCA by eigendecomposition.
  * NOTE the layout: X is N x D row-major with the OBSERVATIONS AS ROWS -- the reference's PCA works on rows (hmatrix
  * meanCovS, PCA.hs:42), unlike its PPCA (D x N).

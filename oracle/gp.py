@@ -55,6 +55,22 @@ def gp_chol_lml(X: np.ndarray, y: np.ndarray, inv_l2: np.ndarray, variance: floa
     return L, lml
 
 
+def gp_posterior_pieces_upper(observe: np.ndarray, x_train: np.ndarray, y_train: np.ndarray):
+    """gpToPosteriorSample up to the random draw, GaussianProcess.hs:59-86, read LITERALLY with hmatrix's `chol`
+    convention: cholSH returns the UPPER factor U (K = U^T U) and linearSolveS solves with it as is.  Returns
+    (mean, posterior_cov_factor_upper) where sample = mean + factor @ normals (:89)."""
+    k_ss = kernel_function(observe, observe)                                   # :61
+    k = kernel_function(x_train, x_train)                                      # :64
+    n = len(x_train)
+    U = np.linalg.cholesky(k + 0.00005 * np.eye(n)).T                          # :67-68 (upper)
+    k_s = kernel_function(observe, x_train)                                    # :71
+    z = np.linalg.solve(U, k_s)                                                # :74  linearSolveS cholK K_s
+    a = np.linalg.solve(U, np.asarray(y_train, dtype=np.float64)[:, None])     # :77
+    mean = (a.T @ z)[0]                                                        # :80
+    post = np.linalg.cholesky(k_ss + 1.0e-6 * np.eye(len(observe)) - z.T @ z).T  # :83-86 (upper)
+    return mean, post
+
+
 def gp_posterior_pieces(observe: np.ndarray, x_train: np.ndarray, y_train: np.ndarray):
     """gpToPosteriorSample up to (not including) the random draw, GaussianProcess.hs:59-86, with the
     factor taken as the LOWER Cholesky factor (SURVEY.md 8a ambiguity note).  Returns

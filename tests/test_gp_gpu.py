@@ -118,3 +118,34 @@ def test_posterior_vs_oracle_larger():
     mean, post, _ = g.gp_to_posterior_sample(xo, xt, yt)
     assert np.max(np.abs(mean - mean_r)) < 1e-6          # K + 5e-5 I has condition number ~1e7
     assert np.max(np.abs(post @ post.T - post_r @ post_r.T)) < 1e-6
+
+
+def test_posterior_upper_factor_reading_reference_example(gp_golden):
+    """The reference read literally with hmatrix's UPPER Cholesky factor (gplvm_gp_posterior_upper): on the reference's own
+    example (5 well separated training points, K ~ I) both readings are defined and differ by ~2e-7 in the mean."""
+    gd = gp_golden
+    rng = np.random.default_rng(4)
+    normals = rng.standard_normal((50, 3))
+    mean_r, post_r = ogp.gp_posterior_pieces_upper(gd["x_test"], gd["x_train"], gd["y_train"])
+    mean, post, samples = g.gp_to_posterior_sample(gd["x_test"], gd["x_train"], gd["y_train"], normals, factor="upper")
+    assert np.max(np.abs(mean - mean_r)) < 1e-9
+    assert not np.any(np.tril(post, -1))                                             # upper factor
+    assert np.max(np.abs(post.T @ post - post_r.T @ post_r)) < 1e-9                  # U^T U (rank deficient: compare the product)
+    assert np.max(np.abs(samples - (mean[:, None] + post @ normals))) < 1e-12       # mean + U normals (GaussianProcess.hs:89)
+    mean_l, _, _ = g.gp_to_posterior_sample(gd["x_test"], gd["x_train"], gd["y_train"])
+    assert 1e-8 < np.max(np.abs(mean - mean_l)) < 1e-3                               # the two readings are different functions
+
+
+def test_posterior_upper_factor_reading_can_fail_where_lower_works():
+    """With correlated training points K_ss - Z^T Z (Z = U^-1 K_s) is not positive definite: the reference's cholSH would
+    throw; the lower reading (the textbook posterior) is fine."""
+    rng = np.random.default_rng(9)
+    xt = np.sort(rng.uniform(-6, 6, 40))
+    yt = np.sin(xt)
+    xo = np.linspace(-5, 5, 61)
+    g.gp_to_posterior_sample(xo, xt, yt)
+    with pytest.raises(np.linalg.LinAlgError):
+        ogp.gp_posterior_pieces_upper(xo, xt, yt)
+    with pytest.raises(g.GplvmError) as ei:
+        g.gp_to_posterior_sample(xo, xt, yt, factor="upper")
+    assert ei.value.code == _lib.ERR_NUMERIC
