@@ -123,59 +123,56 @@ __device__ __forceinline__ double tinv_at(const double* Ls, int i, int j) {
 
 // In-place lower Cholesky of the 128 x 128 SPD matrix in shared memory (lower triangle valid on entry; the strict
 // upper triangle is scratch), blocked by 32 columns:
-//   factor : warp 0 factors the 32 x 32 diagonal block in REGISTERS (lane c = column c, full symmetric block, so
-//            L[c][k] is read from the lane's own registers; pivot and column k travel by shuffles; rsqrt + Newton)
-//   trsm   : one thread per row below solves x L11^T = a by substitution (L11 reads are shared-memory broadcasts)
+//   factor : right-looking Cholesky of the 32 x 32 diagonal block in shared memory by all threads (rsqrt + Newton)
+//   trsm   : one thread per row below solves x L11^T = a in place by substitution (L11 reads are shared-memory broadcasts)
 //   syrk   : 16 x 16 threads, 6 x 6 register tiles, trailing block -= L21 L21^T
 // dinv[j] receives 1 / L[j][j].  Returns (in every thread) false when a pivot is not positive.
 __device__ inline bool block_cholesky_128(double* Ls, double* dinv, int* flag) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int LD = LDS_DIAG;
   if (tid == 0) *flag = 1;
   __syncthreads();
-#pragma unroll 1   // one copy of the (fully unrolled) 32-column step: the kernel stays within the instruction cache
+#pragma unroll 1
   for (int c0 = 0; c0 < NB; c0 += 32) {
-    if (warp == 0) {
-      double m[32];
-#pragma unroll
-      for (int a = 0; a < 32; ++a) m[a] = (a >= lane) ? Ls[(c0 + a) * LD + c0 + lane] : Ls[(c0 + lane) * LD + c0 + a];
-      bool ok = true;
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const double pk = __shfl_sync(0xffffffffu, m[k], k);
-        ok = ok && (pk > 0.0);
-        const double y = rsqrt_nr(pk);
-        const double lck = m[k] * y;
-        if (lane == k) {
-          dinv[c0 + k] = y;
-          Ls[(c0 + k) * LD + c0 + k] = pk * y;
-        }
-#pragma unroll
-        for (int a = k + 1; a < 32; ++a) {
-          const double sa = m[a] * y;
-          if (lane == k) Ls[(c0 + a) * LD + c0 + k] = sa;
-          const double lak = __shfl_sync(0xffffffffu, sa, k);
-          m[a] = fma(-lak, lck, m[a]);
-        }
+    // factor: right-looking Cholesky of the 32 x 32 diagonal block in shared memory by all threads (rolled loops: the
+    // register / shuffle version of round 1 unrolled to 8 544 instructions = 137 KB, refetched on each of the 256 launches)
+    bool ok = true;
+#pragma unroll 1
+    for (int k = 0; k < 32; ++k) {
+      const int kk = c0 + k;
+      __syncthreads();   // the trailing update of step k - 1 (which touched the pivot) is complete
+      const double pk = Ls[kk * LD + kk];
+      ok = ok && (pk > 0.0);
+      const double y = rsqrt_nr(pk);
+      if (tid < 31 - k) Ls[(kk + 1 + tid) * LD + kk] *= y;   // column k below the pivot (nobody reads it before the barrier)
+      __syncthreads();
+      if (tid == 0) {   // the pivot itself is not read again before the factor is copied out
+        dinv[kk] = y;
+        Ls[kk * LD + kk] = pk * y;
       }
-      if (!ok && lane == 0) *flag = 0;
+      const int r = 31 - k;
+      for (int idx = tid; idx < r * r; idx += 256) {
+        const int i = kk + 1 + idx / r, j = kk + 1 + idx % r;
+        if (j <= i) Ls[i * LD + j] = fma(-Ls[i * LD + kk], Ls[j * LD + kk], Ls[i * LD + j]);
+      }
     }
+    if (!ok && tid == 0) *flag = 0;
     __syncthreads();
     const int rb = NB - c0 - 32;  // rows below this block column
-    if (tid < rb) {
-      const int i = c0 + 32 + tid;
-      double x[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = Ls[i * LD + c0 + j];
-#pragma unroll
+    if (tid < rb) {   // trsm, in place: row i of the panel below, x L11^T = a by substitution
+      double* xi = Ls + (c0 + 32 + tid) * LD + c0;
+#pragma unroll 1
       for (int j = 0; j < 32; ++j) {
-        double sacc = x[j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) sacc = fma(-x[k], Ls[(c0 + j) * LD + c0 + k], sacc);
-        x[j] = sacc * dinv[c0 + j];
+        const double* lj = Ls + (c0 + j) * LD + c0;
+        double s0 = xi[j], s1 = 0.0;
+        int k = 0;
+        for (; k + 1 < j; k += 2) {
+          s0 = fma(-xi[k], lj[k], s0);
+          s1 = fma(-xi[k + 1], lj[k + 1], s1);
+        }
+        if (k < j) s0 = fma(-xi[k], lj[k], s0);
+        xi[j] = (s0 + s1) * dinv[c0 + j];
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) Ls[i * LD + c0 + j] = x[j];
     }
     __syncthreads();
     if (rb > 0) {
@@ -243,9 +240,12 @@ __global__ void __launch_bounds__(256, 1) gp_diag_kernel(double* __restrict__ A,
       alpha[k0 + i] = s;
     }
   }
+  __syncthreads();
+  if (tid < nb) dinv[tid] = log(Ls[tid * LDS_DIAG + tid]);   // dinv is free again: one log per thread, summed in order below
+  __syncthreads();
   if (tid == 0) {
     double s = 0.0;
-    for (int i = 0; i < nb; ++i) s += log(Ls[i * LDS_DIAG + i]);
+    for (int i = 0; i < nb; ++i) s += dinv[i];
     state[0] += s;
     if (!ok && state[1] == 0.0) state[1] = (double)(k0 / NB + 1);
   }
