@@ -2,6 +2,8 @@
 // reference layout (Y is D x N feature-major; the device keeps observation-major rows so that one
 // observation is one contiguous, TMA-loadable row), the synthetic workload generator and the EM
 // driver implementing the reference stop rule (src/GPLVM/PPCA.hs:90-92, :173-181).
+#include <thread>
+
 #include "ppca.cuh"
 
 namespace gplvm {
@@ -392,23 +394,38 @@ int gplvm_session_load_host(gplvm_ppca_session* s, const double* Y, int64_t ld) 
   std::lock_guard<std::recursive_mutex> lk(ctx().mu);
   const int64_t D = s->D;
   const int64_t first = s->sh[0].n0;
-  for (ShardState& sh : s->sh) {
-    CUDA_TRY(cudaSetDevice(sh.dev));
+  // One shard: this thread.  Several GPUs driven by one process (gplvm_set_devices): one host thread per shard, so that
+  // every GPU's PCIe link is busy at once (and, for pageable caller memory, the driver's staging copies run in parallel).
+  auto load_shard = [&](ShardState& sh, std::string& err) -> int {
+    if (cudaSetDevice(sh.dev) != cudaSuccess) { err = "cudaSetDevice failed"; return GPLVM_ERR_CUDA; }
     const int64_t ch = std::min(chunk_obs(D), sh.n);
     double* stage = nullptr;
-    CUDA_TRY(cudaMalloc(&stage, sizeof(double) * (size_t)D * ch));
-    for (int64_t c0 = 0; c0 < sh.n; c0 += ch) {
+    cudaError_t e = cudaMalloc(&stage, sizeof(double) * (size_t)D * ch);
+    for (int64_t c0 = 0; e == cudaSuccess && c0 < sh.n; c0 += ch) {
       const int64_t cn = std::min(ch, sh.n - c0);
       const double* src = Y + (sh.n0 - first) + c0;  // (feature 0, observation n0 + c0)
-      cudaError_t e = cudaMemcpy2DAsync(stage, sizeof(double) * ch, src, sizeof(double) * ld, sizeof(double) * cn, D,
-                                        cudaMemcpyHostToDevice, sh.st);
-      if (e != cudaSuccess) { cudaFree(stage); return fail(GPLVM_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+      e = cudaMemcpy2DAsync(stage, sizeof(double) * ch, src, sizeof(double) * ld, sizeof(double) * cn, D, cudaMemcpyHostToDevice, sh.st);
+      if (e != cudaSuccess) break;
       dim3 grid((unsigned)ceil_div(cn, 32), (unsigned)ceil_div(D, 32));
       GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, stage, ch, sh.X + c0 * sh.ldx, sh.ldx, D, cn, 0);
     }
-    CUDA_TRY(cudaStreamSynchronize(sh.st));
-    CUDA_TRY(cudaFree(stage));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sh.st);
+    if (stage) cudaFree(stage);
+    if (e != cudaSuccess) { err = std::string("H2D copy failed: ") + cudaGetErrorString(e); return GPLVM_ERR_CUDA; }
+    return GPLVM_OK;
+  };
+  std::vector<int> rcs(s->sh.size(), GPLVM_OK);
+  std::vector<std::string> errs(s->sh.size());
+  if (s->sh.size() == 1) {
+    rcs[0] = load_shard(s->sh[0], errs[0]);
+  } else {
+    std::vector<std::thread> pool;
+    for (size_t i = 0; i < s->sh.size(); ++i) pool.emplace_back([&, i]() { rcs[i] = load_shard(s->sh[i], errs[i]); });
+    for (std::thread& t : pool) t.join();
+    cudaSetDevice(s->sh[0].dev);
   }
+  for (size_t i = 0; i < rcs.size(); ++i)
+    if (rcs[i] != GPLVM_OK) return fail(rcs[i], "session_load_host: %s", errs[i].c_str());
   s->has_data = true;
   s->initialised = false;
   s->centred = false;
