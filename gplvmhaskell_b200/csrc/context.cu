@@ -162,11 +162,13 @@ int ensure_context() {
 }
 
 void gp_release_workspace();
+void session_release_bounce();
 
 int shutdown_context() {
   Context& c = ctx();
   std::lock_guard<std::recursive_mutex> lk(c.mu);
   gp_release_workspace();
+  session_release_bounce();
   for (Shard& s : c.shards) {
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
@@ -229,7 +231,7 @@ namespace gplvm { const char* last_error_cstr(); }
 extern "C" {
 
 const char* gplvm_last_error(void) { return gplvm::last_error_cstr(); }
-const char* gplvm_version(void) { return "gplvm_b200 0.1 (sm_100a)"; }
+const char* gplvm_version(void) { return "gplvm_b200 0.2 (sm_100a)"; }
 
 int gplvm_set_devices(int n_gpus) {
   using namespace gplvm;

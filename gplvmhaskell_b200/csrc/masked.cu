@@ -722,22 +722,12 @@ int masked_restore(gplvm_ppca_session* s, double* restored, int64_t ld) {
     CUDA_TRY(cudaSetDevice(sh.dev));
     double* fm = sh.scratch + 2 * D;
     GP_LAUNCH(masked_restore_prep_kernel, 1, 256, sizeof(double) * 3 * M * M, sh.st, sh.par, fm);
-    int64_t ch = ((int64_t)32 << 20) / D;
-    ch = std::max<int64_t>(1024, (ch / 32) * 32);
-    ch = std::min(ch, sh.n);
-    double* stage = nullptr;
-    CUDA_TRY(cudaMalloc(&stage, sizeof(double) * (size_t)D * ch));
-    for (int64_t c0 = 0; c0 < sh.n; c0 += ch) {
-      const int64_t cn = std::min(ch, sh.n - c0);
-      GP_LAUNCH(masked_restore_kernel, (unsigned)ceil_div(cn, 256), 256, 0, sh.st, sh.par, sh.EA + c0 * s->EAS + s->NV, s->EAS, fm, stage,
-                ch, cn);
-      double* dst = restored + (sh.n0 - first) + c0;
-      cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * ld, stage, sizeof(double) * ch, sizeof(double) * cn, D,
-                                        cudaMemcpyDeviceToHost, sh.st);
-      if (e != cudaSuccess) { cudaFree(stage); return fail(GPLVM_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); }
-      CUDA_TRY(cudaStreamSynchronize(sh.st));
-    }
-    CUDA_TRY(cudaFree(stage));
+    GP_TRY(session_d2h_rows(sh, D, sh.n, restored + (sh.n0 - first), ld, (int)s->sh.size(),
+                            [&](int64_t c0, int64_t cn, double* stage, int64_t pitch) -> int {
+                              GP_LAUNCH(masked_restore_kernel, (unsigned)ceil_div(cn, 256), 256, 0, sh.st, sh.par,
+                                        sh.EA + c0 * s->EAS + s->NV, s->EAS, fm, stage, pitch, cn);
+                              return GPLVM_OK;
+                            }));
   }
   return GPLVM_OK;
 }

@@ -1,5 +1,7 @@
 // ppca.cuh -- PPCA session state shared by dense.cu / dense_dmma.cu / masked.cu / session.cu.
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 
 namespace gplvm {
@@ -139,6 +141,12 @@ int session_allreduce_stats(gplvm_ppca_session* s, size_t count);
 int session_setup_p2p(gplvm_ppca_session* s);
 int session_peer_allreduce_stats(gplvm_ppca_session* s);   // dense.cu: in-place all-reduce of sh.stats over peer memory
 void session_release_p2p(gplvm_ppca_session* s);
+// Drain a feature-major device producer into a host matrix (D rows, row stride ld doubles, this shard's n columns starting at
+// dst).  produce(c0, cn, stage, pitch) enqueues on sh.st the kernels that fill stage[d * pitch + i], i < cn, for the
+// observations [c0, c0 + cn).  Two stage buffers and a copy stream overlap the kernels with the D2H copies; pageable caller
+// memory goes through pinned bounce buffers drained by several host threads.
+int session_d2h_rows(ShardState& sh, int64_t D, int64_t n, double* dst, int64_t ld, int nshards,
+                     const std::function<int(int64_t, int64_t, double*, int64_t)>& produce);
 int launch_reduce_partials(ShardState& sh, int64_t S, int nparts, double* dst = nullptr, double* scal = nullptr);  // scal: S_DONE skip flag block, default the session's
 
 // Generic split-K statistics GEMM shared by dense.cu and masked.cu (defined in dense.cu).

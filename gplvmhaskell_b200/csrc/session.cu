@@ -80,6 +80,21 @@ __global__ void set_scal_kernel(double* scal, int idx0, double v0, int idx1, dou
   if (idx1 >= 0) scal[idx1] = v1;
 }
 
+// pinned bounce buffers of the pageable-memory load path, two per device, kept until gplvm_dist_finalize / a new context
+struct Bounce { void* p = nullptr; size_t bytes = 0; };
+Bounce g_bounce[64][2];
+std::mutex g_bounce_mu;
+double* bounce_get(int dev, int slot, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_bounce_mu);
+  Bounce& b = g_bounce[dev & 63][slot & 1];
+  if (b.p && b.bytes < bytes) { cudaFreeHost(b.p); b = Bounce(); }
+  if (!b.p) {
+    if (cudaHostAlloc(&b.p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); b = Bounce(); return nullptr; }
+    b.bytes = bytes;
+  }
+  return static_cast<double*>(b.p);
+}
+
 int64_t chunk_obs(int64_t D) {
   int64_t c = ((int64_t)32 << 20) / (D > 0 ? D : 1);  // <= 256 MB staging
   c = (c / 32) * 32;
@@ -102,6 +117,96 @@ void free_shard(ShardState& sh) {
 }
 
 }  // namespace
+
+static bool host_pageable(const void* p) {
+  cudaPointerAttributes attr{};
+  const bool pg = (cudaPointerGetAttributes(&attr, p) != cudaSuccess) || attr.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  return pg;
+}
+static int host_threads(size_t nshards) {
+  return std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / (int)std::max<size_t>(1, nshards)));
+}
+// rows d = 0 .. D-1: copy `bytes` from src + d * src_ld to dst + d * dst_ld with HT threads (rows interleaved over the threads)
+static void threaded_rows_copy(double* dst, int64_t dst_ld, const double* src, int64_t src_ld, int64_t D, size_t bytes, int HT) {
+  auto work = [&](int t) {
+    for (int64_t d = t; d < D; d += HT) memcpy(dst + d * dst_ld, src + d * src_ld, bytes);
+  };
+  if (HT <= 1) { work(0); return; }
+  std::vector<std::thread> pool;
+  for (int t = 1; t < HT; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (std::thread& th : pool) th.join();
+}
+
+int session_d2h_rows(ShardState& sh, int64_t D, int64_t n, double* dst, int64_t ld, int nshards,
+                     const std::function<int(int64_t, int64_t, double*, int64_t)>& produce) {
+  CUDA_TRY(cudaSetDevice(sh.dev));
+  const bool pageable = host_pageable(dst);
+  const int HT = host_threads((size_t)nshards);
+  int64_t ch = pageable ? ((int64_t)8 << 20) / D : ((int64_t)32 << 20) / D;   // 64 MB bounce buffers / 256 MB direct copies
+  ch = std::min(std::max<int64_t>(1024, (ch / 32) * 32), n);
+  double* stage[2] = {nullptr, nullptr};
+  double* bounce[2] = {nullptr, nullptr};
+  cudaEvent_t prod[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+  cudaStream_t cs = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaMalloc(&stage[i], sizeof(double) * (size_t)D * ch);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&prod[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+    if (e == cudaSuccess && pageable) {
+      bounce[i] = bounce_get(sh.dev, i, sizeof(double) * (size_t)D * ch);
+      if (!bounce[i]) e = cudaErrorMemoryAllocation;
+    }
+  }
+  int rc = GPLVM_OK;
+  int64_t chunk = 0, prev_c0 = 0, prev_cn = 0;
+  for (int64_t c0 = 0; e == cudaSuccess && rc == GPLVM_OK && c0 < n; c0 += ch, ++chunk) {
+    const int b = (int)(chunk & 1);
+    const int64_t cn = std::min(ch, n - c0);
+    if (chunk >= 2) e = cudaStreamWaitEvent(sh.st, copied[b], 0);   // stage[b] has been copied out
+    if (e != cudaSuccess) break;
+    rc = produce(c0, cn, stage[b], ch);
+    if (rc != GPLVM_OK) break;
+    e = cudaEventRecord(prod[b], sh.st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, prod[b], 0);
+    if (e != cudaSuccess) break;
+    if (!pageable) {
+      e = cudaMemcpy2DAsync(dst + c0, sizeof(double) * ld, stage[b], sizeof(double) * ch, sizeof(double) * cn, D, cudaMemcpyDeviceToHost, cs);
+    } else {
+      e = cudaMemcpyAsync(bounce[b], stage[b], sizeof(double) * (size_t)D * ch, cudaMemcpyDeviceToHost, cs);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(copied[b], cs);
+    if (e == cudaSuccess && pageable && chunk >= 1) {   // drain the previous chunk on the host while this one is on the wire
+      e = cudaEventSynchronize(copied[b ^ 1]);
+      if (e == cudaSuccess) threaded_rows_copy(dst + prev_c0, ld, bounce[b ^ 1], ch, D, sizeof(double) * (size_t)prev_cn, HT);
+    }
+    prev_c0 = c0; prev_cn = cn;
+  }
+  if (e == cudaSuccess && rc == GPLVM_OK) e = cudaStreamSynchronize(cs);
+  if (e == cudaSuccess && rc == GPLVM_OK && pageable && chunk >= 1)
+    threaded_rows_copy(dst + prev_c0, ld, bounce[(chunk - 1) & 1], ch, D, sizeof(double) * (size_t)prev_cn, HT);
+  cudaStreamSynchronize(sh.st);
+  for (int i = 0; i < 2; ++i) {
+    if (stage[i]) cudaFree(stage[i]);
+    if (prod[i]) cudaEventDestroy(prod[i]);
+    if (copied[i]) cudaEventDestroy(copied[i]);
+  }
+  if (cs) cudaStreamDestroy(cs);
+  if (rc != GPLVM_OK) return rc;
+  if (e != cudaSuccess) return fail(GPLVM_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  return GPLVM_OK;
+}
+
+void session_release_bounce() {
+  std::lock_guard<std::mutex> lk(g_bounce_mu);
+  for (auto& dev : g_bounce)
+    for (Bounce& b : dev) {
+      if (b.p) cudaFreeHost(b.p);
+      b = Bounce();
+    }
+}
 
 int session_allreduce_stats(gplvm_ppca_session* s, size_t count) {
   std::vector<double*> bufs;
@@ -396,8 +501,46 @@ int gplvm_session_load_host(gplvm_ppca_session* s, const double* Y, int64_t ld) 
   const int64_t first = s->sh[0].n0;
   // One shard: this thread.  Several GPUs driven by one process (gplvm_set_devices): one host thread per shard, so that
   // every GPU's PCIe link is busy at once (and, for pageable caller memory, the driver's staging copies run in parallel).
+  // Pageable caller memory (what a Haskell ForeignPtr or a std::vector is): cudaMemcpy2D would stage it through the driver's
+  // single-threaded bounce copy at ~10 GB/s.  Instead `HT` host threads copy the strided rows of a chunk into one of two
+  // pinned bounce buffers while the previous chunk is on the wire.
+  const bool pageable = host_pageable(Y);
+  const int HT = host_threads(s->sh.size());
   auto load_shard = [&](ShardState& sh, std::string& err) -> int {
     if (cudaSetDevice(sh.dev) != cudaSuccess) { err = "cudaSetDevice failed"; return GPLVM_ERR_CUDA; }
+    if (pageable) {
+      const int64_t cb = std::min<int64_t>(std::max<int64_t>(1024, ((int64_t)8 << 20) / D), sh.n);   // <= 64 MB per bounce buffer
+      double* bounce[2] = {nullptr, nullptr};
+      double* stage[2] = {nullptr, nullptr};
+      cudaEvent_t done[2] = {nullptr, nullptr};
+      cudaError_t e = cudaSuccess;
+      for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        bounce[i] = bounce_get(sh.dev, i, sizeof(double) * (size_t)D * cb);   // cached across calls: pinning costs ~0.3 ms per MB
+        if (!bounce[i]) e = cudaErrorMemoryAllocation;
+        if (e == cudaSuccess) e = cudaMalloc(&stage[i], sizeof(double) * (size_t)D * cb);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+      }
+      int64_t chunk = 0;
+      for (int64_t c0 = 0; e == cudaSuccess && c0 < sh.n; c0 += cb, ++chunk) {
+        const int b = (int)(chunk & 1);
+        const int64_t cn = std::min(cb, sh.n - c0);
+        if (chunk >= 2) e = cudaEventSynchronize(done[b]);   // the H2D copy that last used this bounce buffer has finished
+        if (e != cudaSuccess) break;
+        threaded_rows_copy(bounce[b], cb, Y + (sh.n0 - first) + c0, ld, D, sizeof(double) * (size_t)cn, HT);
+        e = cudaMemcpyAsync(stage[b], bounce[b], sizeof(double) * (size_t)D * cb, cudaMemcpyHostToDevice, sh.st);
+        if (e == cudaSuccess) e = cudaEventRecord(done[b], sh.st);
+        if (e != cudaSuccess) break;
+        dim3 grid((unsigned)ceil_div(cn, 32), (unsigned)ceil_div(D, 32));
+        GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, stage[b], cb, sh.X + c0 * sh.ldx, sh.ldx, D, cn, 0);
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(sh.st);
+      for (int i = 0; i < 2; ++i) {
+        if (stage[i]) cudaFree(stage[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+      }
+      if (e != cudaSuccess) { err = std::string("H2D copy (pageable path) failed: ") + cudaGetErrorString(e); return GPLVM_ERR_CUDA; }
+      return GPLVM_OK;
+    }
     const int64_t ch = std::min(chunk_obs(D), sh.n);
     double* stage = nullptr;
     cudaError_t e = cudaMalloc(&stage, sizeof(double) * (size_t)D * ch);
@@ -440,21 +583,12 @@ int gplvm_session_read_data(gplvm_ppca_session* s, double* Y, int64_t ld) {
   // a dense session keeps Xc = X - mean resident; hand back X (equal to the input up to one rounding)
   if (s->centred) GP_TRY(dense_centre(s, +1.0));
   for (ShardState& sh : s->sh) {
-    CUDA_TRY(cudaSetDevice(sh.dev));
-    const int64_t ch = std::min(chunk_obs(D), sh.n);
-    double* stage = nullptr;
-    CUDA_TRY(cudaMalloc(&stage, sizeof(double) * (size_t)D * ch));
-    for (int64_t c0 = 0; c0 < sh.n; c0 += ch) {
-      const int64_t cn = std::min(ch, sh.n - c0);
-      dim3 grid((unsigned)ceil_div(cn, 32), (unsigned)ceil_div(D, 32));
-      GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, sh.X + c0 * sh.ldx, sh.ldx, stage, ch, cn, D, 1);
-      double* dst = Y + (sh.n0 - first) + c0;
-      cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * ld, stage, sizeof(double) * ch, sizeof(double) * cn, D,
-                                        cudaMemcpyDeviceToHost, sh.st);
-      if (e != cudaSuccess) { cudaFree(stage); return fail(GPLVM_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); }
-      CUDA_TRY(cudaStreamSynchronize(sh.st));
-    }
-    CUDA_TRY(cudaFree(stage));
+    GP_TRY(session_d2h_rows(sh, D, sh.n, Y + (sh.n0 - first), ld, (int)s->sh.size(),
+                            [&](int64_t c0, int64_t cn, double* stage, int64_t pitch) -> int {
+                              dim3 grid((unsigned)ceil_div(cn, 32), (unsigned)ceil_div(D, 32));
+                              GP_LAUNCH(transpose_kernel, grid, 256, 0, sh.st, sh.X + c0 * sh.ldx, sh.ldx, stage, pitch, cn, D, 1);
+                              return GPLVM_OK;
+                            }));
   }
   if (s->centred) GP_TRY(dense_centre(s, -1.0));
   return GPLVM_OK;
