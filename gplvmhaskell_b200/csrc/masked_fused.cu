@@ -16,6 +16,7 @@
 //   outputs  : ez = M_i^-1 b, A_i = ez ez^T + sigma^2 M_i^-1.
 // b_i (and |y_c|^2 for the likelihood) come from the TMA + DMMA pass in dense_dmma.cu (MODE_MASKED_B).
 #include "masked_fx.cuh"
+#include "masked_sweeps.cuh"
 #include "ppca.cuh"
 #include "tma.cuh"
 
@@ -64,7 +65,8 @@ struct SolveCfg {
 template <int DD, bool LL, int LPR>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32, SolveCfg<LPR>::MINB)
 masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ yy, const uint32_t* __restrict__ mbits, int64_t n_obs,
-                    Par p, double* __restrict__ EA, double* __restrict__ partials, uint32_t* __restrict__ eamax) {
+                    Par p, double* __restrict__ EA, double* __restrict__ partials, uint32_t* __restrict__ eamax,
+                    const double* __restrict__ gate) {
   using SC = SolveCfg<LPR>;
   constexpr int CPL = SC::CPL, ROWS = SC::ROWS, WPS = SC::WPS, NZ = SC::NZ;
   constexpr int WPRT = DD / 32;
@@ -73,6 +75,7 @@ masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ 
   static_assert(MS_STRIDE >= EAP && EAP >= EASF, "[vech A | ez] rows must fit in the staging area");
   static_assert(DD % 4 == 0, "list region size");
   if (!LL && p.scal[S_DONE] != 0.0) return;
+  if (!LL && gate != nullptr && *gate == 1.0) return;   // the tensor-core Gram solver (masked_gram_tc.cu) took this step
   extern __shared__ __align__(16) double sm[];
   double* Ws = sm;                               // (DD + NZ) x WPS : rows of W; rows DD .. = 0 (list / bucket padding)
   double* Msm = Ws + (DD + NZ) * WPS;            // per warp: ROWS staged matrices [+ index lists]
@@ -206,42 +209,11 @@ masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ 
     // every feature missing: unsupported by the reference (Util.hs:81); flagged, outputs zeroed below
     const bool empty = nmiss >= DD;
     if (empty && j == 0) set_err(p.scal, 2.0);
-    // ---- (d) in-place inverse by symmetric sweeps: after sweeping k = 0..15 the matrix is -M_i^-1 ------------------
-    // Step k (pivot p = M[k][k], d = 1/p):  B[i][l] = M[i][l] - M[i][k] M[k][l] d,  B[i][k] = M[i][k] d,  B[k][k] = -d.
-    // A lane reads M[k][c] from its own columns by symmetry; only column k travels (width-LPR shuffles from its owner).
-    // The owner keeps column k UNSCALED and remembers d in `scale` (applied once at the end), which keeps the update
-    // formula identical in every lane (r = 0 makes it a no-op for the owner's column) -- no per-entry selects.
+    // ---- (d) in-place inverse by symmetric sweeps (masked_sweeps.cuh): m becomes the lane's columns of M_i^-1 ---------
     bool ok = true;
     double pprod = 1.0;
-    double scale[CPL];
-#pragma unroll
-    for (int q = 0; q < CPL; ++q) scale[q] = 1.0;
-#pragma unroll
-    for (int k = 0; k < MF; ++k) {
-      const int qk = k / LPR, jk = k % LPR;
-      const double pk = __shfl_sync(FULL, m[qk][k], jk, LPR);
-      ok = ok && (pk > 0.0);
-      if (LL) pprod *= pk;
-      const double d = rcp_nr(pk);
-      double rr[CPL];
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) rr[q] = (q == qk && j == jk) ? 0.0 : m[q][k] * d;
-#pragma unroll
-      for (int a = 0; a < MF; ++a) {
-        if (a == k) continue;
-        const double ca = __shfl_sync(FULL, m[qk][a], jk, LPR);
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) m[q][a] = fma(-ca, rr[q], m[q][a]);
-      }
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) m[q][k] = (q == qk && j == jk) ? -1.0 : rr[q];
-      if (j == jk) scale[qk] = d;
-    }
+    sweep_invert16<LPR, LL>(m, j, ok, pprod);
     if (!ok && j == 0) set_err(p.scal, 1.0);
-#pragma unroll
-    for (int q = 0; q < CPL; ++q)
-#pragma unroll
-      for (int a = 0; a < MF; ++a) m[q][a] *= -scale[q];      // now column j + LPR q of M_i^-1
     // ---- (e) ez = M_i^-1 b ;  A_i = ez ez^T + s2 M_i^-1 ---------------------------------------------------------------
     double ez[CPL], bown[CPL];
 #pragma unroll
@@ -452,38 +424,50 @@ int launch_miss_dmma(ShardState& sh, int rb, int64_t rows_per_cta, int64_t Spart
 }
 
 template <int DD, bool LL, int LPR>
-int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid) {
+int launch_solve(ShardState& sh, const double* bsrc, const double* yy, int grid, const double* gate) {
   constexpr int smem = SolveCfg<LPR>::smem_bytes(DD);
   static bool attr_done[64] = {};
   if (!attr_done[sh.dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute((masked_solve_kernel<DD, LL, LPR>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done[sh.dev & 63] = true;
   }
-  if (!LL && sh.eamax) CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 24, sh.st));   // class maxima + precision-guard counters
+  // class maxima + precision-guard counters (gated: the tensor-core solver cleared them and may have written the maxima)
+  if (!LL && sh.eamax && !gate) CUDA_TRY(cudaMemsetAsync(sh.eamax, 0, 24, sh.st));
   GP_LAUNCH((masked_solve_kernel<DD, LL, LPR>), grid, SOLVE_WARPS * 32, smem, sh.st, bsrc, yy, sh.mbits, sh.n, sh.par, sh.EA, sh.partials,
-            LL ? nullptr : sh.eamax);
+            LL ? nullptr : sh.eamax, gate);
   return GPLVM_OK;
 }
 
 // 4 lanes per observation (8 observations per warp, 1 CTA per SM): 12.6 ms at N = 2^23 against 13.6 ms for 8 lanes per
 // observation at 2 CTAs per SM (round-2 measurement, profiles/r2_masked_summary.md)
 template <int DD>
-int dispatch_solve(ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out) {
+int dispatch_solve(ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out, const double* gate) {
   constexpr int LPR = 4;
   int grid = (int)std::min<int64_t>(SolveCfg<LPR>::MINB * sm_count(sh.dev), ceil_div(sh.n, SOLVE_WARPS * SolveCfg<LPR>::ROWS));
   if (grid > sh.nparts) grid = sh.nparts;
   if (grid_out) *grid_out = grid;
-  return ll ? launch_solve<DD, true, LPR>(sh, bsrc, yy, grid) : launch_solve<DD, false, LPR>(sh, bsrc, yy, grid);
+  return ll ? launch_solve<DD, true, LPR>(sh, bsrc, yy, grid, nullptr) : launch_solve<DD, false, LPR>(sh, bsrc, yy, grid, gate);
 }
 
 }  // namespace
 
 // E-step solve (ll = false) or likelihood terms (ll = true; per-CTA sums land in sh.partials[0 .. *grid_out))
 int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc, const double* yy, bool ll, int* grid_out) {
+  // E-step at D = 256: Gram matrices from the tcgen05 fixed-point product (masked_gram_tc.cu); the FP64 DMMA solver below is
+  // launched behind it and runs only when the precision gate of that path is closed.  GPLVM_GRAM_DMMA=1: FP64 DMMA only.
+  static const bool force_dmma = []() {
+    const char* e = getenv("GPLVM_GRAM_DMMA");
+    return e ? (atoi(e) != 0) : false;
+  }();
+  const double* gate = nullptr;
+  if (!ll && !force_dmma && s->D == 256 && s->M == 16 && sh.gramB && sh.gramT) {
+    GP_TRY(masked_gram_tc_solve(s, sh, bsrc));
+    gate = sh.gramT + masked_gram_tc_gate_index();
+  }
   switch (s->D) {
-    case 64: return dispatch_solve<64>(sh, bsrc, yy, ll, grid_out);
-    case 128: return dispatch_solve<128>(sh, bsrc, yy, ll, grid_out);
-    case 256: return dispatch_solve<256>(sh, bsrc, yy, ll, grid_out);
+    case 64: return dispatch_solve<64>(sh, bsrc, yy, ll, grid_out, gate);
+    case 128: return dispatch_solve<128>(sh, bsrc, yy, ll, grid_out, gate);
+    case 256: return dispatch_solve<256>(sh, bsrc, yy, ll, grid_out, gate);
     default: return fail(GPLVM_ERR_STATE, "fused masked solver: unsupported D");
   }
 }

@@ -68,6 +68,8 @@ struct ShardState {
   uint32_t* mbitsT = nullptr;  // masked fused path: D x nwT words, bit j of word w = observation 32 w + j misses the feature
   int64_t nwT = 0;             //   4 x ceil(n / 128) words per feature
   uint32_t* eamax = nullptr;   // masked fused path: 256 B block: class maxima of the last solve, precision-guard counters, guard flags (masked_fx.cuh)
+  uint8_t* gramB = nullptr;    // masked tensor-core Gram solver (masked_gram_tc.cu): byte-plane image of W (x) W, rebuilt every step
+  double* gramT = nullptr;     //   its scale / C0 tables and the precision gate
   double* parblock = nullptr;  // parameter block
   double* stats = nullptr;     // packed statistics (all-reduced), `S` doubles
   double* partials = nullptr;  // nparts x S
@@ -129,6 +131,11 @@ int masked_fused_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc
 int masked_fused_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
 int masked_utc_prepare(gplvm_ppca_session* s, ShardState& sh);
 int masked_utc_miss_sums(gplvm_ppca_session* s, ShardState& sh, double* dst);
+// masked_gram_tc.cu: E-step solve with tcgen05 fixed-point Gram matrices (D = 256, M = 16); gate: gramT + masked_gram_tc_gate_index()
+int masked_gram_tc_solve(gplvm_ppca_session* s, ShardState& sh, const double* bsrc);
+size_t masked_gram_tc_image_bytes();
+size_t masked_gram_tc_table_bytes();
+int masked_gram_tc_gate_index();
 int masked_dmma_s2(gplvm_ppca_session* s, ShardState& sh, const double* ez, int64_t ldez, double* dst);
 int dense_dmma_nparts(const gplvm_ppca_session* s, const ShardState& sh);
 // masked.cu

@@ -104,7 +104,7 @@ int64_t chunk_obs(int64_t D) {
 
 void free_shard(ShardState& sh) {
   cudaSetDevice(sh.dev);
-  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.mbitsT); cudaFree(sh.eamax); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
+  cudaFree(sh.X); cudaFree(sh.Ez); cudaFree(sh.EA); cudaFree(sh.mbits); cudaFree(sh.mbitsT); cudaFree(sh.eamax); cudaFree(sh.gramB); cudaFree(sh.gramT); cudaFree(sh.yy); cudaFree(sh.parblock); cudaFree(sh.stats);
   cudaFree(sh.partials); cudaFree(sh.scratch);
   if (sh.tmap) free(sh.tmap);
   if (sh.ev0) cudaEventDestroy(sh.ev0);
@@ -433,6 +433,12 @@ int gplvm_session_create(int64_t D, int64_t N_global, int64_t M, int missing, in
       sh.nwT = 4 * ceil_div(sh.n, (int64_t)128);
       e = cudaMalloc(&sh.mbitsT, sizeof(uint32_t) * (size_t)D * sh.nwT);
       if (e == cudaSuccess) e = cudaMalloc(&sh.eamax, 256);
+      if (e == cudaSuccess && D == 256 && s->M == 16) {
+        e = cudaMalloc(&sh.gramB, masked_gram_tc_image_bytes());
+        if (e == cudaSuccess) e = cudaMemset(sh.gramB, 0, masked_gram_tc_image_bytes());   // padding rows of the last chunk stay zero
+        if (e == cudaSuccess) e = cudaMalloc(&sh.gramT, masked_gram_tc_table_bytes());
+        if (e == cudaSuccess) e = cudaMemset(sh.gramT, 0, masked_gram_tc_table_bytes());
+      }
     }
     if (e == cudaSuccess) e = cudaMalloc(&sh.parblock, sizeof(double) * parlen);
     if (e == cudaSuccess) e = cudaMemset(sh.parblock, 0, sizeof(double) * parlen);
