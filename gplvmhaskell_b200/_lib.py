@@ -75,6 +75,7 @@ SIGNATURES = {
     "gplvm_session_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "gplvm_session_last_steps_ms": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
     "gplvm_session_last_segments_ms": (C.c_int, [C.c_void_p, _c_double_p, C.c_int, _c_int_p]),
+    "gplvm_session_masked_solver_path": (C.c_int, [C.c_void_p, _c_int_p]),
     "gplvm_session_segment_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "gplvm_kernel_launches": (C.c_int64, []),
     "gplvm_probe_dmma_tflops": (C.c_int, [_c_double_p]),

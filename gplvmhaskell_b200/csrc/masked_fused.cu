@@ -243,10 +243,9 @@ masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ 
         for (int q = 0; q < CPL; ++q) {
           const int c = j + LPR * q;
           const double v = empty ? 0.0 : fma(ea, ez[q], s2 * m[q][a]);
-          if (a >= c) {
-            srow[a * (a + 1) / 2 + c] = v;
-            if (valid) mxa = max(mxa, (uint32_t)__double2hiint(v) & 0x7fffffffu);
-          }
+          if (a >= c) srow[a * (a + 1) / 2 + c] = v;
+          // A_i is positive semi-definite: its largest |entry| is on the diagonal
+          if (a == c && valid) mxa = max(mxa, (uint32_t)__double2hiint(v) & 0x7fffffffu);
         }
       }
 #pragma unroll

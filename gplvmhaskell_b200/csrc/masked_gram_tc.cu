@@ -283,18 +283,28 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
     };
-    if (iters > 0) build_A((int64_t)blockIdx.x);
+    // missing-feature count of observation `nq0 + lane` (conversion role), fetched one tile ahead
+    auto count_missing = [&](int64_t tile) {
+      const int64_t n = tile * GT_TILE + 32 * q + lane;
+      int c = 0;
+      if (n < n_obs) {
+        const uint4* mp = reinterpret_cast<const uint4*>(mbits + n * WPRT);
+        const uint4 m0 = mp[0], m1 = mp[1];
+        c = __popc(m0.x) + __popc(m0.y) + __popc(m0.z) + __popc(m0.w) + __popc(m1.x) + __popc(m1.y) + __popc(m1.z) + __popc(m1.w);
+      }
+      return c;
+    };
+    int cnt_next = 0;
+    if (iters > 0) {
+      build_A((int64_t)blockIdx.x);
+      cnt_next = count_missing((int64_t)blockIdx.x);
+    }
 
     for (int64_t it = 0; it < iters; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
       const int64_t nq0 = tile * GT_TILE + 32 * q;   // first observation of this quadrant
       // ---- (a) conversion role: lane = observation nq0 + lane -----------------------------------------------------------
-      int cnt = 0;
-      if (nq0 + lane < n_obs) {
-        const uint4* mp = reinterpret_cast<const uint4*>(mbits + (nq0 + lane) * WPRT);
-        const uint4 m0 = mp[0], m1 = mp[1];
-        cnt = __popc(m0.x) + __popc(m0.y) + __popc(m0.z) + __popc(m0.w) + __popc(m1.x) + __popc(m1.y) + __popc(m1.z) + __popc(m1.w);
-      }
+      const int cnt = cnt_next;
       const long long off = (long long)cnt << GT_FXP;
       double* srow_c = Sq + lane * GT_PITCH;
 #pragma unroll 1
@@ -330,7 +340,10 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
         }
       }
       // every MMA of this tile has completed (t_full of its last chunk): the A operand is free for the next tile
-      if (it + 1 < iters) build_A(tile + gridDim.x);
+      if (it + 1 < iters) {
+        build_A(tile + gridDim.x);
+        cnt_next = count_missing(tile + gridDim.x);
+      }
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // both warps of the quadrant have staged their entries
 
       // ---- (b) sweep role: two rounds of 8 observations -----------------------------------------------------------------
@@ -385,10 +398,9 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
           for (int qq = 0; qq < 4; ++qq) {
             const int cc = j + 4 * qq;
             const double v = empty ? 0.0 : fma(ea, ez[qq], s2 * m[qq][a]);
-            if (a >= cc) {
-              srow[a * (a + 1) / 2 + cc] = v;
-              if (valid) mxa = max(mxa, (uint32_t)__double2hiint(v) & 0x7fffffffu);
-            }
+            if (a >= cc) srow[a * (a + 1) / 2 + cc] = v;
+            // A_i is positive semi-definite: its largest |entry| is on the diagonal
+            if (a == cc && valid) mxa = max(mxa, (uint32_t)__double2hiint(v) & 0x7fffffffu);
           }
         }
         if (valid) {

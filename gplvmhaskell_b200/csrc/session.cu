@@ -810,6 +810,28 @@ int gplvm_session_last_segments_ms(gplvm_ppca_session* s, double* ms_out, int ca
   return GPLVM_OK;
 }
 
+int gplvm_session_masked_solver_path(gplvm_ppca_session* s, int* path_out) {
+  if (!s || !path_out) return fail(GPLVM_ERR_ARG, "null argument");
+  std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+  *path_out = -1;
+  if (!s->missing || s->steps < 1) return GPLVM_OK;
+  if (!s->use_dmma) { *path_out = 0; return GPLVM_OK; }
+  *path_out = 1;
+  static const bool force_dmma = []() {
+    const char* e = getenv("GPLVM_GRAM_DMMA");
+    return e ? (atoi(e) != 0) : false;
+  }();
+  ShardState& sh = s->sh[0];
+  if (sh.gramT && !force_dmma) {
+    double gate = 0.0;
+    CUDA_TRY(cudaSetDevice(sh.dev));
+    CUDA_TRY(cudaStreamSynchronize(sh.st));
+    CUDA_TRY(cudaMemcpy(&gate, sh.gramT + masked_gram_tc_gate_index(), sizeof gate, cudaMemcpyDeviceToHost));
+    if (gate == 1.0) *path_out = 2;
+  }
+  return GPLVM_OK;
+}
+
 const char* gplvm_session_segment_name(gplvm_ppca_session* s, int i) {
   if (!s || i < 0) return "";
   if (s->missing) return i < 6 ? kMaskedSegments[i] : "";

@@ -293,6 +293,12 @@ class Session:
         _lib.check(self.lib.gplvm_session_last_segments_ms(self.h, buf, 16, C.byref(n)))
         return [(self.lib.gplvm_session_segment_name(self.h, i).decode(), buf[i]) for i in range(n.value)]
 
+    def masked_solver_path(self) -> int:
+        """2: tcgen05 fixed-point Gram solver, 1: FP64 DMMA Gram solver, 0: generic path, -1: no masked step yet."""
+        p = C.c_int()
+        _lib.check(self.lib.gplvm_session_masked_solver_path(self.h, C.byref(p)))
+        return p.value
+
     def last_steps_ms(self):
         t, k = C.c_double(), C.c_double()
         _lib.check(self.lib.gplvm_session_last_steps_ms(self.h, C.byref(t), C.byref(k)))

@@ -217,6 +217,12 @@ int gplvm_session_last_steps_ms(gplvm_ppca_session* s, double* total_ms, double*
 int gplvm_session_last_segments_ms(gplvm_ppca_session* s, double* ms_out, int capacity, int* n_out);
 const char* gplvm_session_segment_name(gplvm_ppca_session* s, int i);
 
+/* Which per-observation solver ran the LAST masked E-step of this session (emStepsMissed.stepOne, src/GPLVM/PPCA.hs:106-117):
+ *   2 = Gram matrices from exact fixed-point products on the tcgen05 tensor cores (D = 256, M = 16; masked_gram_tc.cu),
+ *   1 = Gram matrices from the FP64 DMMA product (fused path, or the precision gate of path 2 closed for that step),
+ *   0 = generic CUDA-core path;  -1 = not a masked session / no step yet.   Blocks until that step is done. */
+int gplvm_session_masked_solver_path(gplvm_ppca_session* s, int* path_out);
+
 /* How this session combines the per-step statistics of the ranks: 0 = single GPU (nothing to combine), 1 = one packed
  * ncclAllReduce per step, 2 = all-reduce fused into the library's reduction kernel over NVLink peer memory (direct peer
  * access or CUDA IPC mappings; dense fused path; GPLVM_NO_P2P=1 forces 1). */

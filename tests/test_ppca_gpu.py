@@ -360,3 +360,61 @@ def test_reinit_restarts_from_new_parameters():
         s.steps(4)
         b = s.params()
     assert np.array_equal(a["W"], b["W"]) and a["sigma2"] == b["sigma2"] and b["steps"] == 4
+
+
+# ---------------------------------------------------------------------------------------------------
+# masked E-step: tcgen05 fixed-point Gram solver (masked_gram_tc.cu) and its precision gate
+# ---------------------------------------------------------------------------------------------------
+def _masked_session_steps(Y, W0, steps):
+    d, n = Y.shape
+    with g.Session(d, n, W0.shape[1], missing=True) as s:
+        s.load_host(Y)
+        s.init(W0, 1.0)
+        s.steps(steps)
+        p = s.params()
+        return p, s.masked_solver_path(), s.loglik(), s.restored()
+
+
+def test_missing_gram_tc_path_and_column_scales():
+    """D = 256, M = 16 runs the tensor-core Gram solver (path 2).  Latent columns of W0 spread over 2^-6 .. 2^6: every column
+    has its own fixed-point exponent (diagonal scaling, masked_gram_tc.cu), so the result must stay at the FP64 tolerances
+    against the oracle (stepOne / stepTwo, src/GPLVM/PPCA.hs:106-147)."""
+    Y, W0 = synth(256, 3000, 16, seed=123, nan_prob=0.25)
+    W0 = W0 * np.exp2(np.linspace(-6, 6, 16))[None, :]
+    ref = oppca.em_steps_missed_vectorised(Y, W0, 1.0, ("left", 1))   # 2 steps
+    p, path, ll, restored = _masked_session_steps(Y, W0, 2)
+    assert path == 2
+    assert rel(p["W"], ref.W) < 1e-9, rel(p["W"], ref.W)
+    assert abs(p["sigma2"] - ref.variance) < TOL_SCALAR * ref.variance
+    assert abs(ll - ref.final_exp_likelihood) < TOL_SCALAR * abs(ref.final_exp_likelihood)
+    assert rel(restored, ref.restored_matrix) < TOL_RESTORED
+
+
+def test_missing_gram_tc_gate_closes_on_badly_scaled_column():
+    """A latent column whose entries lie 2^30 below its largest one (> 1 % of the non-zero entries of W more than 2^20 below
+    their column maximum) closes the precision gate: the step is taken by the FP64 DMMA solver (path 1), same tolerances."""
+    Y, W0 = synth(256, 2048, 16, seed=321, nan_prob=0.2)
+    W0[:, 3] *= 2.0 ** -30
+    W0[17, 3] = 1.5
+    ref = oppca.em_steps_missed_vectorised(Y, W0, 1.0, ("left", 0))   # 1 step
+    p, path, ll, restored = _masked_session_steps(Y, W0, 1)
+    assert path == 1
+    assert rel(p["W"], ref.W) < 1e-9, rel(p["W"], ref.W)
+    assert abs(p["sigma2"] - ref.variance) < TOL_SCALAR * ref.variance
+    # the next step starts from a W without the bad column scaling only if EM repaired it; either way the path is reported per step
+    assert rel(restored, ref.restored_matrix) < TOL_RESTORED
+
+
+def test_missing_gram_tc_ragged_tail_and_heavy_masks():
+    """N not a multiple of the 128-observation tile, 60 % NaN (up to ~180 missing features per observation: every byte plane
+    of the fixed-point products is exercised), one observation with nothing missing and one with a single feature left."""
+    Y, W0 = synth(256, 128 * 3 + 77, 16, seed=55, nan_prob=0.6)
+    Y[:, 10] = np.where(np.isnan(Y[:, 10]), 0.25, Y[:, 10])
+    Y[1:, 200] = np.nan
+    ref = oppca.em_steps_missed_vectorised(Y, W0, 1.0, ("left", 1))
+    p, path, ll, restored = _masked_session_steps(Y, W0, 2)
+    assert path == 2
+    assert rel(p["W"], ref.W) < 1e-9, rel(p["W"], ref.W)
+    assert abs(p["sigma2"] - ref.variance) < TOL_SCALAR * ref.variance
+    assert abs(ll - ref.final_exp_likelihood) < TOL_SCALAR * abs(ref.final_exp_likelihood)
+    assert rel(restored, ref.restored_matrix) < TOL_RESTORED
