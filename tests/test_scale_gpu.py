@@ -203,3 +203,22 @@ def test_host_copies_multi_chunk_round_trip():
             assert not np.isnan(R).any()
             restored[pinned] = R.copy()
     assert np.array_equal(restored[False], restored[True])
+
+
+def test_masked_tensor_core_solver_is_deterministic():
+    """N = 2^17 + 5 (1025 tiles of 128 observations: ~7 per persistent CTA, so the TMEM and operand buffers of
+    masked_solve_tc_kernel wrap many times): two runs from the same state give bit-identical parameters and restored data,
+    i.e. no result depends on the timing of the producer / consumer hand-offs (stepOne, src/GPLVM/PPCA.hs:106-117)."""
+    N = (1 << 17) + 5
+    W0 = np.random.default_rng(11).standard_normal((D, M))
+    outs = []
+    with g.Session(D, N, M, missing=True) as s:
+        s.synth(777, 0.2)
+        for _ in range(2):
+            s.init(W0, 1.0)
+            s.steps(2)
+            p = s.params()
+            assert s.masked_solver_path() == 2
+            outs.append((p["W"].copy(), p["mu"].copy(), p["sigma2"], s.restored()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][3], outs[1][3])
