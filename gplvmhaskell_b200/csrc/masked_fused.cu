@@ -5,15 +5,15 @@
 // Reference: emStepsMissed.stepOne, src/GPLVM/PPCA.hs:106-117 (M_i = sigma^2 I + W_i^T W_i, invMP, expXi) and the
 // per-observation log-likelihood terms of PPCA.hs:149-159 (through the determinant lemma).
 //
-// Mapping: one warp per group of 8 observations.
+// Mapping: one warp per group of 8 observations (details at the kernel).  This is the FP64 DMMA solver: it serves the likelihood
+// pass, D = 64 / 128, and any E-step whose tensor-core Gram path (masked_gram_tc.cu, the default at D = 256) has its precision
+// gate closed.
 //   build    : M_i = C0 - W_miss^T W_miss (complement form: work ~ #missing).  The missing-feature indices are compacted
 //              from the packed mask bits; the Gram matrix is a K-compacted mma.sync.m8n8k4.f64 product whose operands
-//              are gathered rows of W in shared memory (W is D x 16, pitch 18 doubles).
+//              are gathered rows of W in shared memory (W is D x 16, pitch 18 doubles), one observation at a time.
 //   then one QUAD of lanes per observation, each lane owning 4 columns of the symmetric 16 x 16 matrix in registers:
-//   invert   : 16 symmetric sweeps (Gauss-Jordan on the SPD matrix, pivots = Schur complements > 0) turn the
-//              registers into -M_i^-1; lane c reads M[k][c] from its OWN column by symmetry, only column k travels
-//              by __shfl_sync; reciprocals by rcp.approx.f64 + 2 Newton steps; log det M_i = sum log pivots.
-//   outputs  : ez = M_i^-1 b, A_i = ez ez^T + sigma^2 M_i^-1.
+//   invert   : 16 symmetric sweeps (masked_sweeps.cuh).
+//   outputs  : ez = M_i^-1 b, A_i = ez ez^T + sigma^2 M_i^-1, rows [vech A | ez] staged and stored as one coalesced block.
 // b_i (and |y_c|^2 for the likelihood) come from the TMA + DMMA pass in dense_dmma.cu (MODE_MASKED_B).
 #include "masked_fx.cuh"
 #include "masked_sweeps.cuh"
