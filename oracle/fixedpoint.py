@@ -160,3 +160,49 @@ def dense_stats_i8(Xc: np.ndarray, W: np.ndarray, sigma2: float, cache: dict) ->
     xez = _to_float(pair_product(Xp, Epl, 7)) * 2.0 ** -(54 + 62) * c[:, None] * se[None, :]
     ee = _to_float(pair_product([e.T for e in Epl], Epl, 7)) * 2.0 ** -124 * se[:, None] * se[None, :]
     return np.concatenate([xez.ravel(), ee.ravel()])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Gram matrices of the masked E-step on the INT8 tensor cores (gplvmhaskell_b200/csrc/masked_gram_tc.cu)
+#   M_i = C0 - G_i,  G_i[a][c] = sum_{d missing in observation i} W[d][a] W[d][c]      (emStepsMissed.stepOne, PPCA.hs:106-117)
+# ---------------------------------------------------------------------------------------------------------------------
+def gram_column_exponents(W: np.ndarray) -> np.ndarray:
+    """e_a with 2^e_a > max_d |W[d][a]| (ilogb + 1), 0 for an all-zero column: what gram_planes_kernel computes."""
+    cmax = np.max(np.abs(W), axis=0)
+    e = np.zeros(W.shape[1], dtype=np.int64)
+    nz = cmax > 0
+    e[nz] = np.floor(np.log2(cmax[nz])).astype(np.int64) + 1
+    # log2 of a float just below a power of two may round up: ilogb semantics are restored by one comparison
+    e[nz & (np.ldexp(1.0, (e - 1).astype(np.int32)) > cmax)] -= 1
+    return e
+
+
+def gram_gate_open(W: np.ndarray, guard_bits: int = 20) -> bool:
+    """Precision gate of the tensor-core Gram path: at most 1 % of the non-zero entries of W more than 2^guard_bits below their
+    column maximum, and column exponents within +-400."""
+    e = gram_column_exponents(W)
+    a = np.abs(W)
+    nz = a > 0
+    small = nz & (a < np.ldexp(1.0, (e - 1 - guard_bits).astype(np.int32))[None, :])
+    return bool(np.all(np.abs(e) < 400) and small.sum() * 100 <= nz.sum())
+
+
+def gram_fixed_point(W: np.ndarray, miss: np.ndarray) -> np.ndarray:
+    """G[a][c] for ONE observation (miss: boolean over the D features) the device way: every product W[d][a] W[d][c] is
+    computed in FP64 (one rounding), scaled by the exact power of two 2^(51 - e_a - e_c), rounded to an integer x, offset to
+    u = x + 2^51 and cut into 7 byte planes; the planes of the missing features are summed exactly, the integer
+    sum_s 256^s S_s - 2^51 cnt is converted to FP64 with one rounding and scaled back by 2^(e_a + e_c - 51)."""
+    D, M = W.shape
+    e = gram_column_exponents(W)
+    G = np.zeros((M, M))
+    cnt = int(np.count_nonzero(miss))
+    Wm = W[np.asarray(miss, dtype=bool)]
+    for a in range(M):
+        for c in range(a + 1):
+            prod = Wm[:, a] * Wm[:, c]                                         # FP64 product, as on the device
+            y = prod * float(np.ldexp(1.0, FXP - int(e[a]) - int(e[c]))) + MAGIC   # device: one FMA; the scaling is exact
+            u = y.view(np.uint64) - np.uint64(0x4330000000000000)
+            S = planes(u).astype(np.int64).sum(axis=0)                       # exact plane sums (s32 accumulators in TMEM)
+            T = sum(int(S[s]) << (8 * s) for s in range(NSL)) - (cnt << FXP)   # exact 64-bit integer
+            G[a, c] = G[c, a] = float(T) * float(np.ldexp(1.0, int(e[a]) + int(e[c]) - FXP))
+    return G

@@ -248,3 +248,40 @@ def test_dense_statistics_in_byte_planes_track_fp64_over_em_steps():
         Wb, s2b, _, _ = oppca.dense_update_from_stats(fx.dense_stats_i8(Xc, Wb, s2b, cache), tot, n, Wb, s2b)
     assert abs(s2a - s2b) < 1e-12 * s2a
     assert np.max(np.abs(Wa - Wb)) < 1e-12 * np.max(np.abs(Wa))
+
+
+def test_fixed_point_gram_matches_fp64_gram():
+    """The tensor-core Gram path of the masked E-step (masked_gram_tc.cu; stepOne, src/GPLVM/PPCA.hs:106-117): the exact
+    integer sum of the rounded products is within one rounding per term (2^-52 of the column-pair scale) of the exactly
+    rounded sum, for well-scaled W and for latent columns spread over 2^-12 .. 2^12."""
+    import math
+    import oracle.fixedpoint as fx
+    rng = np.random.default_rng(42)
+    D, M = 256, 16
+    for spread in (0, 12):
+        W = rng.standard_normal((D, M)) * np.exp2(np.linspace(-spread, spread, M))[None, :]
+        assert fx.gram_gate_open(W)
+        e = fx.gram_column_exponents(W)
+        assert np.all(np.max(np.abs(W), axis=0) < np.exp2(e)) and np.all(np.max(np.abs(W), axis=0) >= np.exp2(e - 1))
+        for frac in (0.0, 0.2, 0.9, 1.0):
+            miss = rng.random(D) < frac
+            G = fx.gram_fixed_point(W, miss)
+            Wm = W[miss]
+            for a in range(M):
+                for c in range(a + 1):
+                    exact = math.fsum((Wm[:, a] * Wm[:, c]).tolist())       # exactly rounded sum of the FP64 products
+                    scale = 2.0 ** (int(e[a]) + int(e[c]))
+                    assert abs(G[a, c] - exact) <= (miss.sum() + 1) * 2.0 ** -52 * scale, (spread, frac, a, c)
+            assert np.array_equal(G, G.T)
+
+
+def test_fixed_point_gram_gate():
+    import oracle.fixedpoint as fx
+    rng = np.random.default_rng(43)
+    W = rng.standard_normal((256, 16))
+    assert fx.gram_gate_open(W)
+    W[:, 3] *= 2.0 ** -30
+    W[17, 3] = 1.5            # 255 of 4096 non-zero entries lie 2^30 below their column maximum: > 1 %
+    assert not fx.gram_gate_open(W)
+    W2 = rng.standard_normal((256, 16)) * 1e-200     # exponents outside +-400: the power-of-two scales would leave the normal range
+    assert not fx.gram_gate_open(W2)
