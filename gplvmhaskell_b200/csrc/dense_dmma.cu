@@ -49,8 +49,11 @@ struct Cfg {
 enum StatsMode {
   MODE_DENSE = 0,      // Ez = Xc proj ; XEz += Xc^T Ez ; EE += Ez^T Ez                       (dense EM step / dense LL pass)
   MODE_MASKED_B = 1,   // b_i = sum_{d observed} w_d (y_id - mu_d), yy_i = sum_{d obs} (y_id - mu_d)^2 -> HBM (PPCA.hs:117)
-  MODE_MASKED_S2 = 2   // S2 += X0^T Ez with X0 = Y, NaN -> 0 and Ez read from HBM             (PPCA.hs:136)
+  MODE_MASKED_S2 = 2,  // S2 += X0^T Ez with X0 = Y, NaN -> 0 and Ez read from HBM             (PPCA.hs:136)
+  MODE_MASKED_BE = 3   // MODE_MASKED_B without yy_i: the E-step only needs b_i (yy_i enters the likelihood, PPCA.hs:149-159),
+                       // and its two DFMA per k-step share the FP64 datapath with the DMMAs
 };
+__host__ __device__ constexpr bool mode_is_b(int mode) { return mode == MODE_MASKED_B || mode == MODE_MASKED_BE; }
 
 // proj     : D x 16 row-major projection (DENSE: A = W Minv or W; MASKED_B: W)
 // partials : gridDim.x x S doubles; per CTA [XEz D x 16 | EE 16 x 16] (DENSE) or [S2 D x 16] (MASKED_S2)
@@ -108,17 +111,17 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
   // step-1 A^T fragments: proj[feature = w FW + 4 ks + t][latent = 8 mt + g], resident for the whole kernel
   constexpr int NP = (MODE == MODE_MASKED_S2) ? 1 : C::KS1;
   double preg[NP][2];
-  double mureg[(MODE == MODE_MASKED_B) ? C::KS1 : 1];
+  double mureg[mode_is_b(MODE) ? C::KS1 : 1];
   if (MODE != MODE_MASKED_S2) {
 #pragma unroll
     for (int ks = 0; ks < NP; ++ks) {
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) preg[ks][mt] = proj[(size_t)(w * C::FW + ks * 4 + t) * MPF + mt * 8 + g];
-      if (MODE == MODE_MASKED_B) mureg[ks] = mu[w * C::FW + ks * 4 + t];
+      if (mode_is_b(MODE)) mureg[ks] = mu[w * C::FW + ks * 4 + t];
     }
   }
 
-  constexpr int NA = (MODE == MODE_MASKED_B) ? 1 : C::MT2;
+  constexpr int NA = mode_is_b(MODE) ? 1 : C::MT2;
   double acc[NA][2][2];  // XEz[feature = w FW + 8 mt + g][latent = 8 nt + 2 t + {0,1}]
 #pragma unroll
   for (int mt = 0; mt < NA; ++mt)
@@ -190,11 +193,13 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
         const uint32_t a0 = xs + chunk_off + s1_thr + (u0 ^ gx4);
         double x0 = lds64(a0);
         double x1 = lds64(a0 + 1024);
-        if (MODE == MODE_MASKED_B) {  // missing -> 0, observed -> y - mu   (PPCA.hs:112-113,117)
+        if (mode_is_b(MODE)) {  // missing -> 0, observed -> y - mu   (PPCA.hs:112-113,117)
           x0 = (x0 == x0) ? x0 - mureg[ks] : 0.0;
           x1 = (x1 == x1) ? x1 - mureg[ks] : 0.0;
-          yacc0 = fma(x0, x0, yacc0);
-          yacc1 = fma(x1, x1, yacc1);
+          if (MODE == MODE_MASKED_B) {
+            yacc0 = fma(x0, x0, yacc0);
+            yacc1 = fma(x1, x1, yacc1);
+          }
         }
         dmma(tp[0][0], preg[ks][0], x0);
         dmma(tp[1][0], preg[ks][1], x0);
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
       }
       __syncthreads();  // S1: partials complete; every warp is also done with step 2 of the previous tile
 
-      if (MODE == MODE_MASKED_B) {  // step 1 was the only reader of this stage: re-arm it right away
+      if (mode_is_b(MODE)) {  // step 1 was the only reader of this stage: re-arm it right away
         if (tid == 0 && i + C::STAGES < ntiles) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           issue(i + C::STAGES);
@@ -238,11 +243,11 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
           sacc.x += v.x;
           sacc.y += v.y;
         }
-        if (MODE == MODE_MASKED_B) {
+        if (mode_is_b(MODE)) {
           const int64_t r = (tile0 + i) * RT + rrow;
           if (r < n_obs) {
             *reinterpret_cast<double2*>(&bout[r * MPF + rlp]) = sacc;
-            if (rlp == 0) yyout[r] = ((yys[rrow] + yys[RT + rrow]) + yys[2 * RT + rrow]) + yys[3 * RT + rrow];
+            if (MODE == MODE_MASKED_B && rlp == 0) yyout[r] = ((yys[rrow] + yys[RT + rrow]) + yys[2 * RT + rrow]) + yys[3 * RT + rrow];
           }
         } else {
           *reinterpret_cast<double2*>(&ezs[rrow * EZ_LD + rlp]) = sacc;
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
       __syncthreads();  // S2: Ez tile complete (MASKED_B: partial tiles free again)
     }
 
-    if (MODE == MODE_MASKED_B) continue;
+    if (mode_is_b(MODE)) continue;
 
     // ---- step 2: XEz += Xc^T . Ez ;  EE += Ez^T . Ez ----------------------------------------------------
 #pragma unroll
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(NW * 32, 2) dense_stats_dmma_kernel(const __gr
       }
     }
   }
-  if (MODE == MODE_MASKED_B) return;
+  if (mode_is_b(MODE)) return;
 
   // ---- epilogue: per-CTA partial statistics ---------------------------------------------------------------
   double* out = partials + (size_t)blockIdx.x * S;
@@ -374,11 +379,11 @@ int dense_dmma_stats(gplvm_ppca_session* s, ShardState& sh, const double* proj) 
   return launch_reduce_partials(sh, s->S, grid);
 }
 
-// b_i = W_obs^T (y_i - mu)_obs and yy_i = |(y_i - mu)_obs|^2 for every local observation (masked E-step / masked LL)
+// b_i = W_obs^T (y_i - mu)_obs and, when yyout is given (masked LL), yy_i = |(y_i - mu)_obs|^2 for every local observation
 int masked_dmma_b(gplvm_ppca_session* s, ShardState& sh, const double* W, const double* mu, double* bout, double* yyout) {
   MaskedArgs ma;
   ma.mu = mu; ma.bout = bout; ma.yyout = yyout;
-  return dispatch_dmma<MODE_MASKED_B>(s, sh, W, 0, ma, nullptr);
+  return yyout ? dispatch_dmma<MODE_MASKED_B>(s, sh, W, 0, ma, nullptr) : dispatch_dmma<MODE_MASKED_BE>(s, sh, W, 0, ma, nullptr);
 }
 
 // dst (D x 16) = sum_i (y_i, NaN -> 0) ez_i^T, ez_i = row i of `ez` (leading dimension ldez)

@@ -651,7 +651,7 @@ int masked_enqueue_step(gplvm_ppca_session* s) {
     double* s2dst = sh.stats + (int64_t)(D + 1) * s->EAS;
     if (s->use_dmma) {
       // fused path (M = 16): b_i by TMA + DMMA, per-observation register solver, sparse complement sums, S2 by DMMA
-      GP_TRY(masked_dmma_b(s, sh, sh.par.W, sh.par.mu, sh.Ez, sh.yy));
+      GP_TRY(masked_dmma_b(s, sh, sh.par.W, sh.par.mu, sh.Ez, nullptr));   // yy_i is only needed by the likelihood pass
       seg_mark(sh, 1);
       GP_TRY(masked_fused_solve(s, sh, sh.Ez, sh.yy, false, nullptr));
       seg_mark(sh, 2);
