@@ -5,10 +5,11 @@
 //   D[f][n] (TMEM, 128 lanes x 144 columns per 128 features)  +=  A[f][k] . B[n][k]      k = observation
 //   A = mask bytes (0 / 1),  B row 7 c + s = byte plane s of column c of [vech A | ez],  B row 133 = 1 (offset count)
 //
-// CTA = (one of 8 groups of 19 columns, observation split); one CTA per SM (2 x 144 TMEM columns for D = 256).
-// Warps 0..7 are PRODUCERS: per 128-observation chunk they expand the staged mask words into the A tile and cut their
-// staged entries into the B tile, both written in the canonical SWIZZLE_128B K-major layout (the layout TMA would
-// write; tools/tcgen05_i8_check.cu pins it), then fence.proxy.async + arrive on full[buffer].  Warp 8 lane 0 is the MMA
+// CTA = (one of 8 groups of 19 columns, observation split); one CTA per SM (2 x 144 accumulator + 2 x 64 A-operand TMEM
+// columns for D = 256).  Warps 0..7 are PRODUCERS: per 128-observation chunk they expand the staged mask words into the
+// A operand IN TENSOR MEMORY (tcgen05.st: lane = feature, 4 observations per 32-bit column; tools/tcgen05_i8_tmem_a_check.cu)
+// and cut their staged entries into the B tile in shared memory, written in the canonical SWIZZLE_128B K-major layout (the
+// layout TMA would write; tools/tcgen05_i8_check.cu pins it), then fence.proxy.async + tcgen05.fence + arrive on full[buffer].  Warp 8 lane 0 is the MMA
 // ISSUER: waits full[b], issues (D / 128) x 4 MMAs (K = 32 each, the K offset goes into the descriptor start address),
 // and tcgen05.commit's to empty[b], which the producers wait on before they overwrite the buffer.  Two operand
 // buffers; entries (flattened, coalesced) and mask words are staged 2 chunks ahead by cp.async.  After the
@@ -35,6 +36,7 @@ constexpr int UT_B_BYTES = UT_N * 128;       // 18 432
 constexpr int UT_STAGE_BYTES = IM_CHUNK * UT_NC * 8;        // staged entries of a chunk: [128 observations][19 columns] FP64
 constexpr int UT_PF = 3;                     // cp.async stages (prefetch distance 2)
 constexpr long long UT_SPIN = 1ll << 26;
+constexpr int UT_NB = 2;                     // operand buffers (B tile in shared memory + A columns in tensor memory); 3: 1.97 vs 1.87 ms at N = 2^22
 static_assert(UT_GROUPS * UT_NC == IM_EAS, "column groups");
 
 // byte (row r, k-byte b) of a K-major operand tile: 128-byte rows, 8-row groups of 1024 B, 16-byte units XOR r & 7
@@ -58,10 +60,16 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity)
 template <int DD>
 struct UtcCfg {
   static constexpr int MT = DD / 128;                       // M = 128 tiles
-  static constexpr int A_BYTES = DD * 128;                  // 32 768 for D = 256
-  static constexpr int BUF_BYTES = A_BYTES + UT_B_BYTES;
-  static constexpr int TMEM_COLS = (MT * UT_N <= 256) ? 256 : 512;
-  static constexpr int SMEM = 2 * BUF_BYTES + UT_PF * UT_STAGE_BYTES + UT_PF * DD * 16 + 1024;
+  // The A operand (mask bytes) lives in TENSOR MEMORY: lane = feature within its 128-row tile, 32-bit column q of a tile =
+  // observations 4 q .. 4 q + 3 of the chunk (tools/tcgen05_i8_tmem_a_check.cu pins this layout); 32 columns per tile and
+  // buffer.  The MMAs then read only B from shared memory (their A reads were half of the operand traffic that kept the
+  // producers' loads and stores waiting), and the producers' 32 KB of A stores per chunk leave the shared-memory pipe.
+  static constexpr int A_COLS = MT * 32;                    // TMEM columns of one A buffer
+  static constexpr int A_BASE = MT * UT_N;                  // first A column (behind the accumulators)
+  static constexpr int BUF_BYTES = UT_B_BYTES;
+  static constexpr int TMEM_COLS = (MT * UT_N + UT_NB * A_COLS <= 256) ? 256 : 512;
+  static_assert(MT * UT_N + UT_NB * A_COLS <= 512, "tensor memory budget");
+  static constexpr int SMEM = UT_NB * BUF_BYTES + UT_PF * UT_STAGE_BYTES + UT_PF * DD * 16 + 1024;
 };
 
 template <int DD>
@@ -73,12 +81,12 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
   if (scal[S_DONE] != 0.0) return;
   extern __shared__ __align__(1024) uint8_t ut_smem_raw[];
   __shared__ uint32_t tmem_base;
-  __shared__ __align__(8) unsigned long long bars[5];   // full[2], empty[2], done
+  __shared__ __align__(8) unsigned long long bars[2 * UT_NB + 1];   // full[NB], empty[NB], done
   __shared__ unsigned long long tred[8 * UT_TASKS * 4 * 2];
   const uint32_t raw_u = smem_u32(ut_smem_raw);
   const uint32_t base_u = (raw_u + 1023u) & ~1023u;      // operand tiles need 1024-byte alignment
   uint8_t* base = ut_smem_raw + (base_u - raw_u);
-  const uint32_t stage_u = base_u + 2 * C::BUF_BYTES;
+  const uint32_t stage_u = base_u + UT_NB * C::BUF_BYTES;
   const uint32_t mask_u = stage_u + UT_PF * UT_STAGE_BYTES;
   const uint32_t bar_u = smem_u32(bars);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -91,18 +99,18 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
   unsigned long long* tp = tpart + (int64_t)blockIdx.x * (2 * UT_NC);
 
   // operand buffers: zero everything (padding rows of B stay zero), count row of B = 1
-  for (int e = tid; e < 2 * C::BUF_BYTES / 16; e += UT_THREADS) reinterpret_cast<uint4*>(base)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tid; e < UT_NB * C::BUF_BYTES / 16; e += UT_THREADS) reinterpret_cast<uint4*>(base)[e] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  for (int e = tid; e < 2 * 32; e += UT_THREADS) {
+  for (int e = tid; e < UT_NB * 32; e += UT_THREADS) {
     const int b = e >> 5, kw = e & 31;
-    *reinterpret_cast<uint32_t*>(base + b * C::BUF_BYTES + C::A_BYTES + sw128(UT_CNT, 4 * kw)) = 0x01010101u;
+    *reinterpret_cast<uint32_t*>(base + b * C::BUF_BYTES + sw128(UT_CNT, 4 * kw)) = 0x01010101u;
   }
   if (tid == 0) {
-    mbar_init(bar_u + 0, UT_PROD);
-    mbar_init(bar_u + 8, UT_PROD);
-    mbar_init(bar_u + 16, 1);
-    mbar_init(bar_u + 24, 1);
-    mbar_init(bar_u + 32, 1);
+    for (int b = 0; b < UT_NB; ++b) {
+      mbar_init(bar_u + 8 * b, UT_PROD);
+      mbar_init(bar_u + 8 * (UT_NB + b), 1);
+    }
+    mbar_init(bar_u + 16 * UT_NB, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -123,30 +131,30 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
       constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(UT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       bool ok = true;
       for (int64_t i = 0; i < my_chunks && ok; ++i) {
-        const int b = (int)(i & 1);
-        ok = mbar_wait_bounded(bar_u + 8 * b, (uint32_t)((i >> 1) & 1));
+        const int b = (int)(i % UT_NB);
+        ok = mbar_wait_bounded(bar_u + 8 * b, (uint32_t)((i / UT_NB) & 1));
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_u = base_u + b * C::BUF_BYTES, b_u = a_u + C::A_BYTES;
+        const uint32_t b_u = base_u + b * C::BUF_BYTES;
+        const uint32_t a_t = tmem + (uint32_t)(C::A_BASE + b * C::A_COLS);
         const uint64_t bdesc = smem_desc_sw128(b_u);
 #pragma unroll
         for (int mt = 0; mt < C::MT; ++mt) {
-          const uint64_t adesc = smem_desc_sw128(a_u + mt * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // K = 32 per instruction: + 32 B inside the swizzle row = + 2 descriptor units
             const uint32_t acc = (i | k) ? 1u : 0u;
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem + (uint32_t)(mt * UT_N)),
-                "l"(adesc + 2 * k), "l"(bdesc + 2 * k), "r"(idesc), "r"(acc), "r"(0u)
+                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem + (uint32_t)(mt * UT_N)),
+                "r"(a_t + (uint32_t)(mt * 32 + 8 * k)), "l"(bdesc + 2 * k), "r"(idesc), "r"(acc), "r"(0u)
                 : "memory");
           }
         }
         // arrives on empty[b] once these MMAs have finished reading the buffer (implies fence::before_thread_sync)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u + 16 + 8 * b) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u + 8 * (UT_NB + b)) : "memory");
       }
       if (!ok) set_err(scal, 3.0);
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u + 32) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u + 16 * UT_NB) : "memory");
     }
   } else {
     // ---------------------------------------------------------------- producers --------------------------------------
@@ -210,32 +218,41 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
     int cs = 0;
     bool ok = true;
     for (int64_t i = 0; i < my_chunks; ++i) {
-      const int b = (int)(i & 1);
+      const int b = (int)(i % UT_NB);
       const int64_t chunk = chunk_begin + i;
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of `chunk` have landed
       asm volatile("bar.sync 1, 256;" ::: "memory");         // ... and everybody's; all producers are done cutting chunk - 1,
       prefetch();                                            // whose stage is the one this prefetch (chunk + 2) overwrites
-      if (i >= 2 && ok) ok = mbar_wait_bounded(bar_u + 16 + 8 * b, (uint32_t)(((i >> 1) - 1) & 1));   // MMAs of chunk i - 2 released the buffer
-      uint8_t* Abuf = base + b * C::BUF_BYTES;
-      const uint32_t b_u = base_u + b * C::BUF_BYTES + C::A_BYTES;
+      if (i >= UT_NB && ok) ok = mbar_wait_bounded(bar_u + 8 * (UT_NB + b), (uint32_t)(((i / UT_NB) - 1) & 1));   // MMAs of chunk i - NB released the buffer
+      const uint32_t b_u = base_u + b * C::BUF_BYTES;
       const uint32_t st = stage_u + (uint32_t)cs * UT_STAGE_BYTES;
       // ---- mask: feature tid, 128 observations: stored word wq, bit 8 b + s  <=>  observation 32 wq + 4 s + b
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   // the MMAs that read A buffer b have completed (empty[b])
       if (tid < DD) {
         uint32_t mw[4];
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(mw[0]), "=r"(mw[1]), "=r"(mw[2]), "=r"(mw[3])
                      : "r"(mask_u + (uint32_t)(cs * DD * 16 + tid * 16)));
-        uint8_t* Arow = Abuf + (tid >> 7) * 16384;
-        const int f = tid & 127;
+        // 16 observations = 4 output words per u: word 4 u + jj = observations 16 u + 4 jj .. + 3 -> TMEM column 4 u + jj
+        uint32_t o[32];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {   // 16 observations = 4 output words: q = 4 u + jj = 8 wq + s
-          uint4 o;
-          o.x = (mw[u >> 1] >> (4 * (u & 1) + 0)) & 0x01010101u;
-          o.y = (mw[u >> 1] >> (4 * (u & 1) + 1)) & 0x01010101u;
-          o.z = (mw[u >> 1] >> (4 * (u & 1) + 2)) & 0x01010101u;
-          o.w = (mw[u >> 1] >> (4 * (u & 1) + 3)) & 0x01010101u;
-          *reinterpret_cast<uint4*>(Arow + sw128(f, 16 * u)) = o;
+        for (int u = 0; u < 8; ++u) {
+          o[4 * u + 0] = (mw[u >> 1] >> (4 * (u & 1) + 0)) & 0x01010101u;
+          o[4 * u + 1] = (mw[u >> 1] >> (4 * (u & 1) + 1)) & 0x01010101u;
+          o[4 * u + 2] = (mw[u >> 1] >> (4 * (u & 1) + 2)) & 0x01010101u;
+          o[4 * u + 3] = (mw[u >> 1] >> (4 * (u & 1) + 3)) & 0x01010101u;
         }
+        // warp w holds features 32 w .. 32 w + 31: TMEM lanes 32 (w & 3) .. of feature tile w >> 2
+        const uint32_t taddr = tmem + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(C::A_BASE + b * C::A_COLS + (w >> 2) * 32);
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+            "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+            "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]),
+            "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]), "r"(o[16]), "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]),
+            "r"(o[21]), "r"(o[22]), "r"(o[23]), "r"(o[24]), "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]),
+            "r"(o[31])
+            : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       // ---- entries: 4 consecutive observations of one column -> 7 plane words
 #pragma unroll
@@ -276,6 +293,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
       }
       cs = (cs + 1 == UT_PF) ? 0 : cs + 1;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // ... and the tensor-memory stores of the A operand
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_u + 8 * b) : "memory");
     }
     if (!ok) set_err(scal, 3.0);
@@ -320,7 +338,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
     tp[tid] = a;
   }
   if (w < 4) {
-    const bool ok = mbar_wait_bounded(bar_u + 32, 0u);
+    const bool ok = mbar_wait_bounded(bar_u + 16 * UT_NB, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (!ok) {
       if (lane == 0) set_err(scal, 3.0);
