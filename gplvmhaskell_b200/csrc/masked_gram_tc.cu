@@ -17,9 +17,12 @@
 //
 // Kernel: persistent, one CTA per SM, tiles of 128 observations.
 //   warp 8 lane 0  : streams the 9 pre-swizzled B chunks (16 entries x 7 planes = 112 rows, K = 256; 28 KB each, written
-//                    by gram_planes_kernel in the canonical SWIZZLE_128B K-major image) through 2 shared-memory buffers with
-//                    cp.async.bulk, and issues 8 MMAs (M = 128, N = 112, K = 32) per chunk into one of 4 TMEM buffers.
-//   warps 0..7     : (a) expand the mask words of the NEXT tile into the A operand (128 x 256 bytes, same layout);
+//                    by gram_planes_kernel in the canonical SWIZZLE_128B K-major image) through 3 shared-memory buffers with
+//                    cp.async.bulk, and issues 8 MMAs (M = 128, N = 112, K = 32; A from tensor memory) per chunk into one of
+//                    4 TMEM accumulator buffers.
+//   warps 0..7     : (a) expand the mask words of the NEXT tile into the A operand IN TENSOR MEMORY (tcgen05.st: lane =
+//                        observation, 4 features per 32-bit column; 64 columns behind the accumulators) -- the MMAs read only B
+//                        from shared memory, and the 32 KB an A tile would take pay for the third B buffer;
 //                    (b) per chunk: tcgen05.ld their TMEM lane quadrant (lane = observation), combine the planes, and
 //                        store M_i entries into the packed lower-triangular staging rows (pitch 137: conflict-free);
 //                        warps w and w + 4 share a quadrant and split the chunk's entries;
@@ -47,17 +50,20 @@ constexpr int GT_D = 256;
 constexpr int GT_KB = GT_D / 128;                  // K blocks of 128 features (one swizzle row each)
 constexpr int GT_KB_BYTES = GT_N * 128;            // 14 336
 constexpr int GT_B_BYTES = GT_KB * GT_KB_BYTES;    // 28 672 per chunk
-constexpr int GT_A_BYTES = GT_KB * 128 * 128;      // 32 768
+constexpr int GT_NBUF = 3;                         // B chunk buffers in shared memory
 constexpr int GT_TILE = 128;                       // observations per tile
 constexpr int GT_PITCH = 137;                      // doubles per staging row (136 entries; odd pitch: conflict-free transposed stores)
 constexpr int GT_STAGE_BYTES = GT_TILE * GT_PITCH * 8;
-constexpr int GT_TBUF = 4, GT_TCOLS = 128;         // TMEM buffers x columns
+constexpr int GT_TBUF = 4, GT_TCOLS = GT_N;        // TMEM accumulator buffers x columns (4 x 112 = 448)
+constexpr int GT_A_COL = GT_TBUF * GT_TCOLS;       // the A operand (mask bytes) lives in TMEM columns [448, 512): lane = observation,
+constexpr int GT_A_COLS = GT_D / 4;                //   32-bit column q = features 4 q .. 4 q + 3 (tools/tcgen05_i8_tmem_a_check.cu)
+static_assert(GT_A_COL + GT_A_COLS <= 512, "tensor memory budget");
 constexpr int GT_SOLVERS = 8;                      // solver warps
 constexpr int GT_THREADS = (GT_SOLVERS + 4) * 32;   // 3 warpgroups: two of solver warps, one whose first warp issues the MMAs
 // register budget (setmaxnreg, per warpgroup): the kernel starts at 168 registers per thread (64 512 for 384 threads);
 // the solver warpgroups grow to 232, the issuer warpgroup shrinks to 40:  8 x 32 x 232 + 4 x 32 x 40 = 64 512
 constexpr int GT_REGS_SOLVER = 232, GT_REGS_ISSUER = 40;
-constexpr int GT_OFF_B = GT_A_BYTES, GT_OFF_STAGE = GT_OFF_B + 2 * GT_B_BYTES, GT_OFF_BAR = GT_OFF_STAGE + GT_STAGE_BYTES;
+constexpr int GT_OFF_B = 0, GT_OFF_STAGE = GT_OFF_B + GT_NBUF * GT_B_BYTES, GT_OFF_BAR = GT_OFF_STAGE + GT_STAGE_BYTES;
 constexpr int GT_SMEM = GT_OFF_BAR + 128;
 // tab block (doubles): [0, 136) scale 2^(ea + ec - 51), [136, 272) C0 entries, [272] gate (1.0: this kernel takes the step)
 constexpr int GT_TAB_C0 = GT_NV, GT_TAB_GATE = 2 * GT_NV, GT_TAB_DOUBLES = 2 * GT_NV + 8;
@@ -187,16 +193,16 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
     if (threadIdx.x == 0) set_err(p.scal, 3.0);
     return;
   }
-  const uint32_t a_u = base_u, b_u = base_u + GT_OFF_B, bar_u = base_u + GT_OFF_BAR;
+  const uint32_t b_u = base_u + GT_OFF_B, bar_u = base_u + GT_OFF_BAR;
   double* stage = reinterpret_cast<double*>(gt_smem + GT_OFF_STAGE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gt_smem + GT_OFF_BAR + 120);
-  // barriers: b_full[2] @0, b_empty[2] @16, t_full[4] @32, t_empty[4] @64, a_full @96
-  const uint32_t b_full = bar_u, b_empty = bar_u + 16, t_full = bar_u + 32, t_empty = bar_u + 64, a_full = bar_u + 96;
+  // barriers: b_full[3] @0, b_empty[3] @24, t_full[4] @48, t_empty[4] @80, a_full @112
+  const uint32_t b_full = bar_u, b_empty = bar_u + 24, t_full = bar_u + 48, t_empty = bar_u + 80, a_full = bar_u + 112;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t ntiles = (n_obs + GT_TILE - 1) / GT_TILE;
   const int64_t iters = (ntiles > (int64_t)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) mbar_init(b_full + 8 * i, 1), mbar_init(b_empty + 8 * i, 1);
+    for (int i = 0; i < GT_NBUF; ++i) mbar_init(b_full + 8 * i, 1), mbar_init(b_empty + 8 * i, 1);
     for (int i = 0; i < GT_TBUF; ++i) mbar_init(t_full + 8 * i, 1), mbar_init(t_empty + 8 * i, GT_SOLVERS);
     mbar_init(a_full, GT_SOLVERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -204,7 +210,7 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (w == GT_SOLVERS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(GT_TBUF * GT_TCOLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -219,32 +225,32 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
       constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(GT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const int64_t total = iters * GT_CHUNKS;
       auto load = [&](int64_t i) {
-        const int buf = (int)(i & 1), c = (int)(i % GT_CHUNKS);
+        const int buf = (int)(i % GT_NBUF), c = (int)(i % GT_CHUNKS);
         mbar_expect_tx(b_full + 8 * buf, (uint32_t)GT_B_BYTES);
         bulk_load_1d(b_u + buf * GT_B_BYTES, Bimg + (size_t)c * GT_B_BYTES, (uint32_t)GT_B_BYTES, b_full + 8 * buf);
       };
-      if (total > 0) load(0);
+      for (int64_t i = 0; i < GT_NBUF - 1 && i < total; ++i) load(i);
       for (int64_t i = 0; i < total; ++i) {
-        const int buf = (int)(i & 1), tb = (int)(i & 3), c = (int)(i % GT_CHUNKS);
-        if (i + 1 < total) {
-          if (i + 1 >= 2) mbar_wait(b_empty + 8 * ((i + 1) & 1), (uint32_t)((((i + 1) >> 1) - 1) & 1));
-          load(i + 1);
+        const int buf = (int)(i % GT_NBUF), tb = (int)(i & 3), c = (int)(i % GT_CHUNKS);
+        const int64_t nx = i + GT_NBUF - 1;   // keep NBUF - 1 chunk loads in flight behind the one being multiplied
+        if (nx < total) {
+          if (nx >= GT_NBUF) mbar_wait(b_empty + 8 * (int)(nx % GT_NBUF), (uint32_t)(((nx / GT_NBUF) - 1) & 1));
+          load(nx);
         }
-        mbar_wait(b_full + 8 * buf, (uint32_t)((i >> 1) & 1));
+        mbar_wait(b_full + 8 * buf, (uint32_t)((i / GT_NBUF) & 1));
         if (i >= GT_TBUF) mbar_wait(t_empty + 8 * tb, (uint32_t)(((i >> 2) - 1) & 1));
         if (c == 0) mbar_wait(a_full, (uint32_t)((i / GT_CHUNKS) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int kb = 0; kb < GT_KB; ++kb) {
-          const uint64_t adesc = smem_desc_sw128(a_u + kb * 16384);
           const uint64_t bdesc = smem_desc_sw128(b_u + buf * GT_B_BYTES + kb * GT_KB_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // K = 32 per instruction: + 32 B inside the swizzle row = + 2 descriptor units
             const uint32_t acc = (kb | k) ? 1u : 0u;
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem + (uint32_t)(tb * GT_TCOLS)),
-                "l"(adesc + 2 * k), "l"(bdesc + 2 * k), "r"(idesc), "r"(acc), "r"(0u)
+                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem + (uint32_t)(tb * GT_TCOLS)),
+                "r"(tmem + (uint32_t)(GT_A_COL + kb * 32 + 8 * k)), "l"(bdesc + 2 * k), "r"(idesc), "r"(acc), "r"(0u)
                 : "memory");
           }
         }
@@ -260,45 +266,42 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
     double* Sq = stage + (size_t)(32 * q) * GT_PITCH;
     const double s2 = p.scal[S_SIGMA2];
     uint32_t mxa = 0u, mxe = 0u;
-    // mask words of a tile -> A operand bytes (1 = missing): pair (r, wd) = observation r of the tile, word wd (32 features)
-    auto build_A = [&](int64_t tile) {
-#pragma unroll
-      for (int mm = 0; mm < (GT_TILE * WPRT) / (GT_SOLVERS * 32); ++mm) {
-        const int pi = (w * 4 + mm) * 32 + lane;
-        const int r = pi >> 3, wd = pi & 7;
-        const int64_t n = tile * GT_TILE + r;
-        const uint32_t bits = (n < n_obs) ? mbits[n * WPRT + wd] : 0u;
-        uint8_t* row = gt_smem + (wd >> 2) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          uint4 o;
-          o.x = (((bits >> (16 * u + 0)) & 0xfu) * 0x00204081u) & 0x01010101u;
-          o.y = (((bits >> (16 * u + 4)) & 0xfu) * 0x00204081u) & 0x01010101u;
-          o.z = (((bits >> (16 * u + 8)) & 0xfu) * 0x00204081u) & 0x01010101u;
-          o.w = (((bits >> (16 * u + 12)) & 0xfu) * 0x00204081u) & 0x01010101u;
-          *reinterpret_cast<uint4*>(row + ((((2 * (wd & 3) + u) ^ (r & 7))) << 4)) = o;
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
-    };
-    // missing-feature count of observation `nq0 + lane` (conversion role), fetched one tile ahead
-    auto count_missing = [&](int64_t tile) {
+    // Mask words of observation `tile * 128 + 32 q + lane` (the lane's conversion-role observation): their population count
+    // is the missing-feature count, and this warp's half of them (features 128 h .. 128 h + 127) becomes the A operand bytes
+    // (1 = missing) of TMEM lane 32 q + lane, columns GT_A_COL + 32 h .. + 31.  Fetched / written one tile ahead.
+    auto build_A = [&](int64_t tile) -> int {
       const int64_t n = tile * GT_TILE + 32 * q + lane;
-      int c = 0;
+      uint4 m0 = make_uint4(0u, 0u, 0u, 0u), m1 = m0;
       if (n < n_obs) {
         const uint4* mp = reinterpret_cast<const uint4*>(mbits + n * WPRT);
-        const uint4 m0 = mp[0], m1 = mp[1];
-        c = __popc(m0.x) + __popc(m0.y) + __popc(m0.z) + __popc(m0.w) + __popc(m1.x) + __popc(m1.y) + __popc(m1.z) + __popc(m1.w);
+        m0 = mp[0];
+        m1 = mp[1];
       }
+      const int c = __popc(m0.x) + __popc(m0.y) + __popc(m0.z) + __popc(m0.w) + __popc(m1.x) + __popc(m1.y) + __popc(m1.z) + __popc(m1.w);
+      const uint4 mh = h ? m1 : m0;
+      const uint32_t wds[4] = {mh.x, mh.y, mh.z, mh.w};
+      uint32_t o[32];
+#pragma unroll
+      for (int wl = 0; wl < 4; ++wl)
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq) o[8 * wl + gq] = (((wds[wl] >> (4 * gq)) & 0xfu) * 0x00204081u) & 0x01010101u;
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(GT_A_COL + 32 * h);
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+          "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+          "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]),
+          "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]), "r"(o[16]), "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]),
+          "r"(o[21]), "r"(o[22]), "r"(o[23]), "r"(o[24]), "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]),
+          "r"(o[31])
+          : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
       return c;
     };
     int cnt_next = 0;
-    if (iters > 0) {
-      build_A((int64_t)blockIdx.x);
-      cnt_next = count_missing((int64_t)blockIdx.x);
-    }
+    if (iters > 0) cnt_next = build_A((int64_t)blockIdx.x);
 
     for (int64_t it = 0; it < iters; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
@@ -340,10 +343,7 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
         }
       }
       // every MMA of this tile has completed (t_full of its last chunk): the A operand is free for the next tile
-      if (it + 1 < iters) {
-        build_A(tile + gridDim.x);
-        cnt_next = count_missing(tile + gridDim.x);
-      }
+      if (it + 1 < iters) cnt_next = build_A(tile + gridDim.x);
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // both warps of the quadrant have staged their entries
 
       // ---- (b) sweep role: two rounds of 8 observations -----------------------------------------------------------------
@@ -441,7 +441,7 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (w == GT_SOLVERS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(GT_TBUF * GT_TCOLS) : "memory");
+  if (w == GT_SOLVERS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
 }  // namespace
