@@ -29,9 +29,12 @@ constexpr int UT_NC = 19;                    // columns per group (8 groups x 19
 constexpr int UT_GROUPS = IM_EAS / UT_NC;
 constexpr int UT_N = 144;                    // MMA N: 19 x 7 planes + count row = 134, padded to a multiple of 16
 constexpr int UT_CNT = UT_NC * NSL;          // row / column index of the offset count (133)
-constexpr int UT_PROD = 256;                 // producer threads
+constexpr int UT_PROD = 320;                 // producer threads: 10 warps x 2 cutting tasks = the 20 (column quad, quad block) tasks
+constexpr int UT_PW = UT_PROD / 32;          // producer warps; warp UT_PW issues the MMAs
 constexpr int UT_THREADS = UT_PROD + 32;
-constexpr int UT_TASKS = 3;                  // (column quad, quad block) tasks per producer thread: 5 x 4 = 20 over 8 warps
+constexpr int UT_TASKS = 2;                  // (column quad, quad block) tasks per producer thread: 5 x 4 = 20 over 10 warps (8 warps x 3 slots left
+                                             // 4 warps one task short and everybody waiting for the others at the chunk barrier)
+static_assert(UT_PW * UT_TASKS >= 20, "cutting tasks");
 constexpr int UT_B_BYTES = UT_N * 128;       // 18 432
 constexpr int UT_STAGE_BYTES = IM_CHUNK * UT_NC * 8;        // staged entries of a chunk: [128 observations][19 columns] FP64
 constexpr int UT_PF = 3;                     // cp.async stages (prefetch distance 2)
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
   extern __shared__ __align__(1024) uint8_t ut_smem_raw[];
   __shared__ uint32_t tmem_base;
   __shared__ __align__(8) unsigned long long bars[2 * UT_NB + 1];   // full[NB], empty[NB], done
-  __shared__ unsigned long long tred[8 * UT_TASKS * 4 * 2];
+  __shared__ unsigned long long tred[UT_PW * UT_TASKS * 4 * 2];
   const uint32_t raw_u = smem_u32(ut_smem_raw);
   const uint32_t base_u = (raw_u + 1023u) & ~1023u;      // operand tiles need 1024-byte alignment
   uint8_t* base = ut_smem_raw + (base_u - raw_u);
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  if (w == 8) {
+  if (w == UT_PW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base;
 
-  if (w == 8) {
+  if (w == UT_PW) {
     // ---------------------------------------------------------------- MMA issuer -------------------------------------
     if (lane == 0) {
       // D = S32, A signed 8 bit, B unsigned 8 bit, both K-major, N = 144, M = 128
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
     const uint32_t hA = eamax[0], hE = eamax[1];
 #pragma unroll
     for (int j = 0; j < UT_TASKS; ++j) {
-      const int id = w + 8 * j, cq = id >> 2;
+      const int id = w + UT_PW * j, cq = id >> 2;
       tcol[j] = (cq < 4) ? 8 * (cq >> 1) + (cq & 1) + 2 * (lane & 3) : 16 + (lane & 3);
       tkq[j] = 8 * (id & 3) + (lane >> 2);
       tval[j] = id < 20 && tcol[j] < UT_NC;
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
     // Staging: the 128 x 19 entries of a chunk are copied element-wise (8-byte cp.async) in flattened order, thread t
     // taking elements t, t + 256, ...: a warp instruction reads 32 consecutive entries (at most 3 rows of the column
     // group) and writes 256 contiguous bytes.  Mask words: thread t copies the 16 bytes of feature t.
-    const int er0 = tid / UT_NC, ec0 = tid % UT_NC;   // element tid = (row er0, column ec0); + 256 = (+ 13 rows, + 9 columns)
+    const int er0 = tid / UT_NC, ec0 = tid % UT_NC;   // element tid = (row er0, column ec0); + UT_PROD = (+ UT_PROD / 19 rows, + UT_PROD % 19 columns)
     const double* pe = EA + chunk_begin * IM_CHUNK * IM_EAS + col0;
     const uint32_t* pm = mT + (chunk_begin * DD + (tid % DD)) * 4;
     int pf_stage = 0;
@@ -200,8 +203,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + (uint32_t)((tid + UT_PROD * m) * 8)),
                          "l"(pe + er * IM_EAS + ec)
                          : "memory");
-          er += 13;
-          ec += 9;
+          er += UT_PROD / UT_NC;
+          ec += UT_PROD % UT_NC;
           if (ec >= UT_NC) ec -= UT_NC, ++er;
         }
         if (tid < DD)
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
       const int b = (int)(i % UT_NB);
       const int64_t chunk = chunk_begin + i;
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of `chunk` have landed
-      asm volatile("bar.sync 1, 256;" ::: "memory");         // ... and everybody's; all producers are done cutting chunk - 1,
+      asm volatile("bar.sync 1, %0;" ::"n"(UT_PROD) : "memory");         // ... and everybody's; all producers are done cutting chunk - 1,
       prefetch();                                            // whose stage is the one this prefetch (chunk + 2) overwrites
       if (i >= UT_NB && ok) ok = mbar_wait_bounded(bar_u + 8 * (UT_NB + b), (uint32_t)(((i / UT_NB) - 1) & 1));   // MMAs of chunk i - NB released the buffer
       const uint32_t b_u = base_u + b * C::BUF_BYTES;
@@ -326,14 +329,14 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
   }
   // ------------------------------------------------------------------ epilogue ---------------------------------------
   __syncthreads();
-  if (tid < 2 * UT_NC) {   // column c lives in column quad cq, lane slot cl; tasks id = 4 cq + kb -> (warp id & 7, slot id >> 3)
+  if (tid < 2 * UT_NC) {   // column c lives in column quad cq, lane slot cl; tasks id = 4 cq + kb -> (warp id % UT_PW, slot id / UT_PW)
     const int c = tid >> 1, h = tid & 1;
     const int cq = (c < 16) ? 2 * (c >> 3) + (c & 1) : 4, cl = (c < 16) ? (c & 7) >> 1 : c - 16;
     unsigned long long a = 0ull;
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
       const int id = 4 * cq + kb;
-      a += tred[(((id & 7) * UT_TASKS + (id >> 3)) * 4 + cl) * 2 + h];
+      a += tred[(((id % UT_PW) * UT_TASKS + (id / UT_PW)) * 4 + cl) * 2 + h];
     }
     tp[tid] = a;
   }
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) masked_miss_utc_kernel(const do
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (w == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
+  if (w == UT_PW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
 }
 
 // dst[f][c] (f < D: complement sums of feature f; f = D: totals over all observations), each rounded to FP64 once
