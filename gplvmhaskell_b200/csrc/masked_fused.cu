@@ -241,6 +241,7 @@ masked_solve_kernel(const double* __restrict__ bsrc, const double* __restrict__ 
         const double ea = __shfl_sync(FULL, ez[a / LPR], a % LPR, LPR);
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
+          if (a < LPR * q) continue;   // compile time: columns j + LPR q > a lie above the diagonal for every lane
           const int c = j + LPR * q;
           const double v = empty ? 0.0 : fma(ea, ez[q], s2 * m[q][a]);
           if (a >= c) srow[a * (a + 1) / 2 + c] = v;

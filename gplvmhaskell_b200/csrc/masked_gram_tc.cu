@@ -396,6 +396,7 @@ masked_solve_tc_kernel(const double* __restrict__ bsrc, const uint32_t* __restri
           const double ea = __shfl_sync(FULL, ez[a / 4], a % 4, 4);
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
+            if (a < 4 * qq) continue;   // compile time: columns j + 4 qq > a lie above the diagonal for every lane
             const int cc = j + 4 * qq;
             const double v = empty ? 0.0 : fma(ea, ez[qq], s2 * m[qq][a]);
             if (a >= cc) srow[a * (a + 1) / 2 + cc] = v;
