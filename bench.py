@@ -67,9 +67,9 @@ FLOP_OBS_MASKED = 52394.0   # complement form, 20 % NaN
 # dram__bytes_write.sum); NOT measured in the bench run itself.
 TRAFFIC_DENSE = ((17.1803136e9 + 5.25e6) / (1 << 23), "profiles/r2_dense_dmma_ncu_raw.csv (ncu --set full capture of "
                  "dense_stats_dmma_kernel<256,0>, 2^23 observations: 17.180 GB read + 5.2 MB written); not measured in this run")
-TRAFFIC_MASKED = (7.341e9 / (1 << 20), "profiles/r2_masked_kernels_ncu_raw.csv (ncu --set full captures of the four masked "
-                  "statistics kernels, 2^20 observations: b pass 2.29 + solver 1.39 + complement sums 1.31 + S2 pass 2.35 GB); "
-                  "not measured in this run")
+TRAFFIC_MASKED = (7.555e9 / (1 << 20), "ncu --set full captures of the four masked statistics kernels, per 2^20 observations: b pass 2.28 + "
+                  "S2 pass 2.35 GB (profiles/r2_masked_kernels_ncu_raw.csv), tensor-core solver 1.42 GB (profiles/r2_solve_tc_ncu_raw.csv, "
+                  "2^21 observations), complement sums 1.51 GB (profiles/r2_utc_ncu_raw.csv, 2^21 observations); not measured in this run")
 
 
 def flops_per_obs_dense(d=D, m=M):
