@@ -117,6 +117,80 @@ __device__ __forceinline__ void tri_inverse_in_place(double* Ls, int nb, const d
   }
   __syncthreads();
 }
+// The same inverse for a full 128 x 128 factor (identity padded), blocked by 32, in place and without scratch:
+//   1. the four diagonal blocks T_II = L_II^-1 by substitution, one thread per column (128 threads, <= 465 multiply-adds each);
+//   2. U_I = T_II L_I[:, 0 .. 32 I) overwrites the off-diagonal part of block row I (L has been copied out; one thread per
+//      column keeps the 32 entries in registers, 192 threads);  then T_II [L_I | L_II] = [U_I | 1], so
+//   3. T_IJ = - sum_{K = J .. I-1} U_IK T_KJ, sub-diagonal by sub-diagonal (2 x 2 entries per thread, 256 threads).
+// The thread-per-column routine above gives its longest thread 8 000 dependent multiply-adds; here no thread has more than
+// ~1 300 (gp_diag_kernel sits on the critical path of the factorisation's last outer steps).  The shared-memory footprint
+// must not grow: the kernel has to fit on an SM beside ONE 92 KB trailing-update CTA (228 - 93 KB), or it waits for an SM to
+// drain completely.  Storage as above: T[i][j], i > j, in Ls[j * LDS_DIAG + i]; the diagonal of T is dinv.
+__device__ inline void tri_inverse_blocked_128(double* Ls, const double* dinv) {
+  constexpr int LD = LDS_DIAG;
+  const int tid = threadIdx.x;
+  if (tid < NB) {
+    const int b0 = tid & ~31, j = tid;
+    const double tjj = dinv[j];
+    const double* hist = Ls + j * LD;
+    for (int i = j + 1; i < b0 + 32; ++i) {
+      const double* Li = Ls + i * LD;
+      double s0 = -Li[j] * tjj, s1 = 0.0;
+      int k = j + 1;
+      for (; k + 1 < i; k += 2) {
+        s0 = fma(-Li[k], hist[k], s0);
+        s1 = fma(-Li[k + 1], hist[k + 1], s1);
+      }
+      if (k < i) s0 = fma(-Li[k], hist[k], s0);
+      Ls[j * LD + i] = (s0 + s1) * dinv[i];
+    }
+  }
+  __syncthreads();
+  if (tid < 192) {   // (I, m): I = 1: m < 32 (tid 0..31); I = 2: m < 64 (tid 32..95); I = 3: m < 96 (tid 96..191)
+    const int I = (tid < 32) ? 1 : ((tid < 96) ? 2 : 3);
+    const int m = tid - ((I == 1) ? 0 : ((I == 2) ? 32 : 96));
+    const int i0 = 32 * I;
+    double col[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) col[k] = Ls[(i0 + k) * LD + m];
+#pragma unroll
+    for (int r = 31; r >= 0; --r) {   // row r needs the original rows k <= r only: descending order, all in registers
+      double u = dinv[i0 + r] * col[r];
+#pragma unroll
+      for (int k = 0; k < r; ++k) u = fma(Ls[(i0 + k) * LD + i0 + r], col[k], u);   // T_II[r][k], a broadcast read
+      Ls[(i0 + r) * LD + m] = u;
+    }
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;   // rows 2 ty + {0, 1}, columns 2 tx + {0, 1} of a 32 x 32 block
+#pragma unroll 1
+  for (int d = 1; d < NB / 32; ++d) {
+#pragma unroll 1
+    for (int J = 0; J + d < NB / 32; ++J) {
+      const int i0 = 32 * (J + d), c0 = 32 * J + 2 * tx, c1 = c0 + 1;
+      const double* Ur0 = Ls + (i0 + 2 * ty) * LD;
+      const double* Ur1 = Ur0 + LD;
+      const double* Tc0 = Ls + c0 * LD;   // T[m][c0] for m > c0
+      const double* Tc1 = Tc0 + LD;
+      double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+      {   // m = c0 and m = c1: the diagonal of T_JJ
+        const double u00 = Ur0[c0], u10 = Ur1[c0], u01 = Ur0[c1], u11 = Ur1[c1];
+        const double d0 = dinv[c0], d1 = dinv[c1], t10 = Tc0[c1];   // T[c1][c0]
+        a00 = fma(u01, t10, u00 * d0); a10 = fma(u11, t10, u10 * d0);
+        a01 = u01 * d1; a11 = u11 * d1;
+      }
+      for (int mm = c1 + 1; mm < i0; ++mm) {
+        const double t0 = Tc0[mm], t1 = Tc1[mm], u0 = Ur0[mm], u1 = Ur1[mm];
+        a00 = fma(u0, t0, a00); a01 = fma(u0, t1, a01);
+        a10 = fma(u1, t0, a10); a11 = fma(u1, t1, a11);
+      }
+      // T_IJ goes to the transposed upper storage; nobody reads these entries in this sub-diagonal pass
+      Ls[c0 * LD + i0 + 2 * ty] = -a00; Ls[c1 * LD + i0 + 2 * ty] = -a01;
+      Ls[c0 * LD + i0 + 2 * ty + 1] = -a10; Ls[c1 * LD + i0 + 2 * ty + 1] = -a11;
+    }
+    __syncthreads();
+  }
+}
 __device__ __forceinline__ double tinv_at(const double* Ls, int i, int j) {
   return (j < i) ? Ls[j * LDS_DIAG + i] : ((i == j) ? 1.0 / Ls[i * LDS_DIAG + i] : 0.0);
 }
@@ -228,7 +302,7 @@ __global__ void __launch_bounds__(256, 1) gp_diag_kernel(double* __restrict__ A,
     if (j <= i) A[(k0 + i) * ld + (k0 + j)] = Ls[i * LDS_DIAG + j];
   }
   __syncthreads();
-  tri_inverse_in_place(Ls, nb, dinv);
+  tri_inverse_blocked_128(Ls, dinv);   // rows / columns past nb are identity: their T entries are 0
   for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int i = e / NB, j = e % NB;
     Tinv[e] = (i < nb && j < nb) ? tinv_at(Ls, i, j) : 0.0;
