@@ -547,7 +547,11 @@ def run_ppca(env: Env, args, n_obs: int, missing: bool, steps: int, warmup: int,
                        "sharding": "observations row-sharded over %d rank(s)" % env.world, "collective": collective,
                        "l2": "inputs (%.1f GB per rank) exceed the 126 MB L2; no flush" % (8 * D * count / 1e9),
                        "init": "W0 ~ N(0,1) seed %d, sigma2_0 = 1" % W0_SEED,
-                       "driver": "gplvm_session_run(Left %d)" % (steps - 1) if left_k_run else "gplvm_session_steps"},
+                       "driver": "gplvm_session_run(Left %d)" % (steps - 1) if left_k_run else "gplvm_session_steps",
+                       **({"arithmetic": "FP64 throughout, except two sums whose one factor is an exact 0/1 mask (per-observation Gram "
+                                         "matrices, per-feature complement sums): every FP64 term is rounded once to a fixed-point grid "
+                                         "(<= 2^-52 of its scale) and the sums are exact integers on the INT8 tensor cores; on-device gates "
+                                         "hand badly scaled steps to the FP64 DMMA kernels (DESIGN.md 4.4)"} if missing else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity_check": parity}
 
